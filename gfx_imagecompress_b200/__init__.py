@@ -1,0 +1,16 @@
+"""gfx_imagecompress_b200 -- B200 (sm_100a) BCn block-compression engine behind the gfx_imagecompress C API.
+
+The product is the shared library `lib/libgfx_imagecompress_b200.so` (CUDA kernels + C-ABI, built in-tree by
+`build.py`).  This package is the thin Python host mirror used by tests / bench: ctypes bindings of the C-ABI
+(`include/b200ic.h`) and of the drop-in `Image_Compress*` API (`include/gfx_imagecompress/imagecompress.h`).
+There is no CPU fallback: importing works without a GPU, encoding raises.
+"""
+from .api import (  # noqa: F401
+    BC1, BC4, BC5, BC6H, BC7_AMD, BC7_RG, BLOCK_BYTES, B200Error, Opts, Image, library, load_library,
+    encode_host, encode_device, encode_blocks, launch_count, init,
+    Image_CompressAMDBC1, Image_CompressAMDBC4, Image_CompressAMDBC5, Image_CompressAMDBC6H, Image_CompressAMDBC7,
+    Image_CompressRichGel999BC7, ImageCompress_Compress,
+    Image_CompressAMDAlphaSingleModeBlock, Image_CompressAMDBC1Block, Image_CompressAMDMultiModeLDRBlock,
+    Image_CompressRichGel999BC7enc16,
+)
+from . import synth  # noqa: F401

@@ -1,0 +1,17 @@
+// kernels.h -- launchers of the per-codec sm_100a kernels (one translation unit per codec so that the
+// bit-exact ones can be built with --fmad=false independently of the tolerance-gated ones).
+#pragma once
+#include "common.cuh"
+
+namespace b200ic {
+
+cudaError_t launch_bc45(const SrcImage &img, int channels, int first_channel, void *dst, cudaStream_t stream);
+cudaError_t launch_bc1(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
+cudaError_t launch_bc7rg(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
+cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
+cudaError_t launch_bc6h(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
+cudaError_t init_bc7rg_tables();
+cudaError_t init_bc7amd_tables();
+cudaError_t init_bc6h_tables();
+
+} // namespace b200ic
