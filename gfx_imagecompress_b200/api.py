@@ -121,6 +121,10 @@ def init(device: int = 0) -> None:
     _check(library().b200ic_init(device), "b200ic_init")
 
 
+def codec_available(codec: int) -> bool:
+    return bool(library().b200ic_codec_available(codec))
+
+
 def launch_count() -> int:
     return int(library().b200ic_launch_count())
 

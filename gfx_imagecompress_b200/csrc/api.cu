@@ -188,6 +188,26 @@ int b200ic_device_count(void) {
 	return n;
 }
 
+int b200ic_codec_available(int codec) {
+	switch (codec) {
+	case B200IC_BC4:
+	case B200IC_BC5: return 1;
+#ifdef B200IC_HAVE_BC1
+	case B200IC_BC1: return 1;
+#endif
+#ifdef B200IC_HAVE_BC7RG
+	case B200IC_BC7_RG: return 1;
+#endif
+#ifdef B200IC_HAVE_BC7AMD
+	case B200IC_BC7_AMD: return 1;
+#endif
+#ifdef B200IC_HAVE_BC6H
+	case B200IC_BC6H: return 1;
+#endif
+	default: return 0;
+	}
+}
+
 int b200ic_init(int device) {
 	t_error.clear();
 	int n = 0;

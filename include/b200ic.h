@@ -86,6 +86,8 @@ B200IC_API void b200ic_shutdown(void);
 /* Last error message of the calling thread ("" if none). */
 B200IC_API const char *b200ic_last_error(void);
 B200IC_API int b200ic_device_count(void);
+/* 1 if kernels for `codec` are built into this library, else 0 (encode calls then fail with an error). */
+B200IC_API int b200ic_codec_available(int codec);
 
 B200IC_API uint32_t b200ic_block_bytes(int codec);
 B200IC_API uint64_t b200ic_output_bytes(int codec, uint32_t width, uint32_t height, uint32_t slices);

@@ -132,5 +132,30 @@ class Restated:
 
 
 class Decoders:
+    """Spec decoders (oracle/bcdec.c): blocks -> texels, for PSNR."""
+
     def __init__(self):
         self.lib = C.CDLL(os.path.join(_REFDIR, "libbcdec.so"))
+        L = self.lib
+        L.bcdec_bc1.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.bcdec_bc7.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.bcdec_bc45.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+
+    def bc1(self, blocks: np.ndarray, w: int, h: int) -> np.ndarray:
+        b = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((h, w, 4), np.uint8)
+        self.lib.bcdec_bc1(b.ctypes.data, w, h, out.ctypes.data)
+        return out
+
+    def bc7(self, blocks: np.ndarray, w: int, h: int, with_modes: bool = False):
+        b = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((h, w, 4), np.uint8)
+        hist = np.zeros(9, np.uint32)
+        self.lib.bcdec_bc7(b.ctypes.data, w, h, out.ctypes.data, hist.ctypes.data)
+        return (out, hist) if with_modes else out
+
+    def bc45(self, blocks: np.ndarray, w: int, h: int, nch: int) -> np.ndarray:
+        b = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((h, w, nch), np.uint8)
+        self.lib.bcdec_bc45(b.ctypes.data, w, h, nch, out.ctypes.data)
+        return out

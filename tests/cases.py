@@ -40,3 +40,37 @@ def random_scalar_blocks(n=4096, seed=0):
             v = rng.choice(np.array([0, 1 / 255, 2 / 255, 254 / 255, 1.0, 0.5, 0.3], np.float32), 16)
         blocks[i] = v
     return blocks
+
+
+def to_blocks_rgba8(img: np.ndarray) -> np.ndarray:
+    """(H, W, 4) uint8 with H, W multiples of 4 -> (nblocks, 16) uint32 packed RGBA8 in block order."""
+    h, w, _ = img.shape
+    return np.ascontiguousarray(img.reshape(h // 4, 4, w // 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(-1, 16, 4)).view(np.uint32).reshape(-1, 16)
+
+
+def rgba_cases(small: bool = False):
+    """(name, (H, W, C) uint8, fmt) colour images for BC1 / BC7: seeded gradient+noise with the alpha layouts of
+    SURVEY.md 8d, the reference's own test patterns (tests/test_imagecompress.cpp:14-126) incl. the NPOT size,
+    white noise, smooth low-contrast ramps and flat blocks."""
+    n = 32 if small else 64
+    rng = np.random.default_rng(11)
+    out = [
+        ("gradnoise_lefthalf", synth.rgba8_gradnoise(n * 2, n, 3, "lefthalf"), synth.FMT_RGBA8),
+        ("gradnoise_opaque", synth.rgba8_gradnoise(n, n, 4, "opaque"), synth.FMT_RGBA8),
+        ("gradnoise_punch", synth.rgba8_gradnoise(n, n, 1, "punch"), synth.FMT_RGBA8),
+        ("gradnoise_npot", synth.rgba8_gradnoise(37, 21, 5, "ramp"), synth.FMT_RGBA8),
+        ("noise_rgba", rng.integers(0, 256, (n // 2, n // 2, 4), dtype=np.uint8), synth.FMT_RGBA8),
+        ("noise_rgb", rng.integers(0, 256, (n // 2, n // 2, 3), dtype=np.uint8), synth.FMT_RGB8),
+    ]
+    for name in ("R", "RGB", "RGB_Punchthrough", "RGBA"):
+        p, f = synth.pattern(name, n, n)
+        out.append(("pattern_" + name, p, f))
+    p, f = synth.pattern("RGB", 33 if small else 257, 33 if small else 257)
+    out.append(("pattern_RGB_npot", p, f))
+    x = np.arange(n)[None, :]
+    y = np.arange(n)[:, None]
+    smooth = np.stack([(x + y) // 2 + 100, (x * 2) % 256 + 0 * y, (y * 3) % 256 + 0 * x, np.full((n, n), 255)], 2).astype(np.uint8)
+    out.append(("smooth_ramps", np.ascontiguousarray(smooth), synth.FMT_RGBA8))
+    lowc = (rng.integers(0, 6, (n // 2, n // 2, 4)) + np.array([120, 60, 200, 250])).astype(np.uint8)
+    out.append(("low_contrast", lowc, synth.FMT_RGBA8))
+    return out
