@@ -1,0 +1,1006 @@
+// bc7amd_core.cuh -- AMD-Compressonator-compatible BC7 encoder search (all eight modes), scalar building blocks.
+//
+// Follows the search of the reference's BC7BlockEncoder at quality = performance = 1.0, colourRestrict =
+// alphaRestrict = true (the only configuration its image API uses, src/amd_bc7_compressor.cpp:58-65):
+//   block set-up / mode filter / mode order      src/amd_bc7_body.cpp:1289-1465
+//   single-index modes 0,1,2,3,6,7               src/amd_bc7_body.cpp:548-890
+//   dual-index modes 4,5                         src/amd_bc7_body.cpp:1059-1278
+//   bit packing                                  src/amd_bc7_body.cpp:333-538, 902-1056
+//   optQuantAnD_d + helpers                      src/amd_bc7_3dquant_vpc.cpp:138-420, 686-695, 1201-1286, 1874-2045
+//   ep_shaker_d / ep_shaker_2_d / single point   src/amd_shake.cpp:351-367, 513-538, 546-1404
+//
+// Differences in construction (results are equal up to sort tie order, see below):
+//   * the reference's 100 MB `ramp[clog][bits][p1][p2][i]` double LUT (src/amd_shake.cpp:225,283-286) is an exact
+//     integer expression of the expanded endpoints (ramp_int below); it is computed in registers.
+//   * the single-colour tables sp_idx / sp_err (src/amd_shake.cpp:230-232,293-345) are packed to 4 bytes per entry
+//     (p1, p2, distance) and built once on the host by build_single_point_table().
+//   * ep_shaker_d's cached per-texel error cube `ce` is recomputed (same operations, same order of additions).
+//   * the outputs nobody reads (reconstructed points `out`, `direction`, `step`, `epo`, ep_shaker_d's endpoint codes
+//     -- overwritten by the ep_shaker_2_d call that always follows) are not produced.
+//   * qsort is replaced by a stable insertion sort; the reference's glibc qsort orders EQUAL keys differently, which
+//     is one reason this path is PSNR-gated and not bit-gated (SURVEY.md 7 hard part 4).
+//   * trace quantiser: never reached at quality 1 (m_blockMaxRange <= 255 always), not built.
+// `real` is the arithmetic type of the search; double reproduces the reference.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define A7_HD __host__ __device__ __forceinline__
+#define A7_HDN __host__ __device__ __noinline__
+#else
+#define A7_HD inline
+#define A7_HDN
+#endif
+#if defined(__CUDA_ARCH__)
+#define B7T_QUAL __constant__ const
+#else
+#define B7T_QUAL const
+#endif
+#include "bc7_tables.h"
+
+namespace b200ic {
+namespace amd7 {
+
+typedef double real;
+#define A7_HUGE DBL_MAX
+
+constexpr int kMaxEntries = 16;
+
+// ---- mode description (bti[], src/amd_bc7_body.cpp:84-94) ---------------------------------------------
+enum Parity { CART = 0, SAME_PAR = 1, BCC = 2 };
+struct ModeInfo {
+	uint8_t alpha;        // 0 none, 1 combined, 2 separate
+	uint8_t partition_bits, rotation_bits, index_mode_bits, scalar_bits, vector_bits, parity, subsets, index_bits0, index_bits1;
+};
+A7_HD ModeInfo mode_info(int m) {
+	switch (m) {
+	case 0: return {0, 4, 0, 0, 0, 12, BCC, 3, 3, 0};
+	case 1: return {0, 6, 0, 0, 0, 18, SAME_PAR, 2, 3, 0};
+	case 2: return {0, 6, 0, 0, 0, 15, CART, 3, 2, 0};
+	case 3: return {0, 6, 0, 0, 0, 21, BCC, 2, 2, 0};
+	case 4: return {2, 0, 2, 1, 6, 15, CART, 1, 2, 3};
+	case 5: return {2, 0, 2, 0, 8, 21, CART, 1, 2, 2};
+	case 6: return {1, 0, 0, 0, 0, 28, BCC, 1, 4, 0};
+	default: return {1, 6, 0, 0, 0, 20, BCC, 2, 2, 0};
+	}
+}
+
+// ---- ramps ---------------------------------------------------------------------------------------------
+// REFERENCE QUIRK (kept for parity): src/amd_shake.cpp tests `#if USE_FINAL_BC7_WEIGHTS` (:236) but only
+// src/amd_bc7_body.cpp defines that macro (:60), so the shakers' ramp table is built with the "pure linear" weights
+// i/(2^clog - 1) (:245-252), not the BC7 hardware weights {0,21,43,64}/64 ... that a decoder applies. Every
+// endpoint / index refinement below therefore optimises against floor(e1 + i/(C-1) * (e2-e1) + 0.5).
+// Exact integer form: the fractional part of the exact value is an odd multiple of 1/(2(C-1)), never within
+// rounding distance of an integer, so the reference's double evaluation and this integer one always agree.
+A7_HD int expand_bits(int bits, int v) { return (v << (8 - bits)) | (v >> (2 * bits - 8)); } // expand_ (:254-257)
+A7_HD int ramp_int(int e1, int e2, int i, int clog) {
+	const int D = (1 << clog) - 1;
+	return (2 * (D * e1 + i * (e2 - e1)) + D) / (2 * D);
+}
+
+// ---- single-colour table ----------------------------------------------------------------------------------
+// entry (clog-2, bits-5, value, par1, par2, index) -> p1 | p2<<8 | distance<<16 ; error = distance^2
+struct Tables {
+	const uint32_t *sp;
+};
+constexpr size_t kSpEntries = 3u * 4u * 256u * 2u * 2u * 16u;
+A7_HD size_t sp_slot(int clog, int bits, int value, int o1, int o2, int i) {
+	return ((((size_t) ((clog - 2) * 4 + (bits - 5)) * 256 + value) * 2 + o1) * 2 + o2) * 16 + i;
+}
+inline void build_single_point_table(uint32_t *sp) { // init_ramps (:293-345)
+	const uint32_t kEmpty = 0xffffffffu;
+	for (size_t i = 0; i < kSpEntries; i++) sp[i] = kEmpty;
+	for (int clog = 2; clog < 5; clog++)
+		for (int bits = 5; bits < 9; bits++) {
+			for (int p1 = 0; p1 < (1 << bits); p1++)
+				for (int p2 = 0; p2 < (1 << bits); p2++)
+					for (int i = 0; i < (1 << clog); i++) {
+						const int v = ramp_int(expand_bits(bits, p1), expand_bits(bits, p2), i, clog);
+						sp[sp_slot(clog, bits, v, p1 & 1, p2 & 1, i)] = (uint32_t) p1 | ((uint32_t) p2 << 8); // last writer wins
+					}
+			for (int o1 = 0; o1 < 2; o1++)
+				for (int o2 = 0; o2 < 2; o2++)
+					for (int i = 0; i < (1 << clog); i++) {
+						bool exact[256];
+						for (int v = 0; v < 256; v++) exact[v] = sp[sp_slot(clog, bits, v, o1, o2, i)] != kEmpty;
+						for (int v = 0; v < 256; v++) {
+							if (exact[v]) continue;
+							int k = 1;
+							for (; k < 256; k++)
+								if ((v - k >= 0 && exact[v - k]) || (v + k < 256 && exact[v + k])) break;
+							uint32_t src = 0;
+							if (v - k >= 0 && exact[v - k]) src = sp[sp_slot(clog, bits, v - k, o1, o2, i)];
+							else if (v + k < 256 && exact[v + k]) src = sp[sp_slot(clog, bits, v + k, o1, o2, i)];
+							sp[sp_slot(clog, bits, v, o1, o2, i)] = (src & 0xffffu) | ((uint32_t) k << 16);
+						}
+					}
+		}
+}
+
+// ---- small utilities ---------------------------------------------------------------------------------------
+// order[] = permutation sorting key[] ascending (stable)
+A7_HD void sort_order(const real *key, int *order, int n) {
+	for (int i = 0; i < n; i++) {
+		const real k = key[i];
+		int j = i;
+		while (j > 0 && key[order[j - 1]] - k > 0) { order[j] = order[j - 1]; j--; }
+		order[j] = i;
+	}
+}
+A7_HD int ilog2(int v) { int c = 0; while (v >>= 1) c++; return c; }
+
+// eigenVector_d (:336-420): dominant eigenvector by repeated squaring, 3 rounds of 8
+A7_HD void dominant_axis(const real cov[4][4], real axis[4], int dim) {
+	real c[2][4][4];
+	for (int i = 0; i < dim; i++)
+		for (int j = 0; j < dim; j++) c[0][i][j] = cov[i][j];
+	int l = 0;
+	for (int round = 0; round < 3; round++) {
+		real md = 0;
+		for (int i = 0; i < dim; i++) md = c[l][i][i] > md ? c[l][i][i] : md;
+		if (md <= 0) return;
+		for (int i = 0; i < dim; i++)
+			for (int j = 0; j < dim; j++) c[l][i][j] /= md;
+		for (int m = 0; m < 8; m++) {
+			for (int i = 0; i < dim; i++)
+				for (int j = 0; j < dim; j++) {
+					real t = 0;
+					for (int k = 0; k < dim; k++) t += c[l][i][k] * c[l][k][j];
+					c[1 - l][i][j] = t;
+				}
+			l = 1 - l;
+		}
+	}
+	real md = 0;
+	int k = 0;
+	for (int i = 0; i < dim; i++) {
+		k = c[l][i][i] > md ? i : k;
+		md = c[l][i][i] > md ? c[l][i][i] : md;
+	}
+	real t = 0;
+	for (int i = 0; i < dim; i++) {
+		t += c[l][k][i] * c[l][k][i];
+		axis[i] = c[l][k][i];
+	}
+	t = sqrt(t);
+	if (t <= 0) return;
+	for (int i = 0; i < dim; i++) axis[i] /= t;
+}
+
+// quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of n scalars (lattice A_n* decoding)
+A7_HD void lattice_quantise(const real *v_, int k, int n, int *idx) {
+	real m = v_[0], M = v_[0];
+	for (int i = 1; i < n; i++) {
+		m = m < v_[i] ? m : v_[i];
+		M = M > v_[i] ? M : v_[i];
+	}
+	if (M == m) {
+		for (int i = 0; i < n; i++) idx[i] = 0;
+		return;
+	}
+	const real s = (real) (k - 1) / (M - m);
+	real d[kMaxEntries];
+	real dm = 0, r = 0;
+	for (int i = 0; i < n; i++) {
+		const real v = v_[i] * s;
+		const real z = floor(v + 0.5 - m * s);
+		idx[i] = (int) z;
+		d[i] = v - z - m * s;
+		dm += d[i];
+		r += d[i] * d[i];
+	}
+	if ((real) n * r - dm * dm >= (real) (n - 1) / 4 / 2) {
+		dm /= (real) n;
+		for (int i = 0; i < n; i++) d[i] -= dm;
+		int ord[kMaxEntries];
+		sort_order(d, ord, n);
+		real mm = 0, l = 0;
+		int j = -1;
+		for (int i = 0; i < n; i++) {
+			l += d[ord[i]] - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
+			if (l < mm) { mm = l; j = i; }
+		}
+		j = (j + 1) % n;
+		for (int i = j; i < n; i++) idx[ord[i]]++;
+	}
+	int mi = idx[0];
+	for (int i = 1; i < n; i++) mi = mi < idx[i] ? mi : idx[i];
+	for (int i = 0; i < n; i++) idx[i] -= mi;
+}
+
+// optQuantAnD_d (:1874-2045): PCA line + iterative optimal uniform quantiser. Returns the SSE; index[] out.
+A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *index, int dim) {
+	real cen[kMaxEntries][4], mean[4], cov[4][4];
+	for (int j = 0; j < dim; j++) {
+		real m = 0;
+		for (int k = 0; k < n; k++) m += data[k][j];
+		if (n) m /= (real) n;
+		mean[j] = m;
+		for (int k = 0; k < n; k++) cen[k][j] = data[k][j] - m;
+	}
+	for (int i = 0; i < dim; i++)
+		for (int j = 0; j <= i; j++) {
+			real c = 0;
+			for (int k = 0; k < n; k++) c += cen[k][i] * cen[k][j];
+			cov[i][j] = c;
+			cov[j][i] = c;
+		}
+	real t = 0;
+	for (int j = 0; j < dim; j++) t += cov[j][j];
+	if (t < (1. / 256.) || n == 0) {
+		for (int i = 0; i < n; i++) index[i] = 0;
+		return 0;
+	}
+	real dir[4] = {0, 0, 0, 0}, proj[kMaxEntries];
+	dominant_axis(cov, dir, dim);
+	for (int k = 0; k < n; k++) {
+		real p = 0;
+		for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
+		proj[k] = p;
+	}
+	int first[kMaxEntries];
+	int try_two = 50;
+	real s;
+	for (int it = 0; it < 200; it++) {
+		if (it) {
+			int done;
+			do {
+				real q = 0;
+				s = t = 0;
+				for (int k = 0; k < n; k++) {
+					s += index[k];
+					t += index[k] * index[k];
+				}
+				for (int j = 0; j < dim; j++) {
+					real d = 0;
+					for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
+					dir[j] = d;
+					q += d * d;
+				}
+				s /= (real) n;
+				t = t - s * s * (real) n;
+				t = (t == 0 ? 0. : 1 / t);
+				q = sqrt(q);
+				t *= q;
+				if (q != 0)
+					for (int j = 0; j < dim; j++) dir[j] /= q;
+				for (int k = 0; k < n; k++) {
+					real p = 0;
+					for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
+					proj[k] = p;
+				}
+				int ord[kMaxEntries];
+				sort_order(proj, ord, n);
+				int k = 0;
+				done = 1;
+				int next[kMaxEntries];
+				for (int j = 0; j < n; j++) {
+					while (proj[ord[j]] > ((real) k + 0.5 - s) * t && k < clusters - 1) k++;
+					next[ord[j]] = k;
+				}
+				for (int j = 0; j < n; j++) {
+					done = done && (next[j] == index[j]);
+					index[j] = next[j];
+				}
+			} while (!done && try_two--);
+			if (it == 1) {
+				for (int j = 0; j < n; j++) first[j] = index[j];
+			} else {
+				done = 1;
+				for (int j = 0; j < n; j++) done = done && (first[j] == index[j]);
+				if (done) break;
+			}
+		}
+		lattice_quantise(proj, clusters, n, index);
+	}
+	s = t = 0;
+	for (int k = 0; k < n; k++) {
+		s += index[k];
+		t += index[k] * index[k];
+	}
+	for (int j = 0; j < dim; j++) {
+		real d = 0;
+		for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
+		dir[j] = d;
+	}
+	s /= (real) n;
+	t = t - s * s * (real) n;
+	t = (t == 0 ? 0. : 1 / t);
+	real err = 0;
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < dim; j++) {
+			const real o = mean[j] + dir[j] * t * ((real) index[i] - s);
+			err += (data[i][j] - o) * (data[i][j] - o);
+		}
+	return err;
+}
+
+// ep_find_floor (:351-367)
+A7_HD int endpoint_floor(real v, int bits, int use_par, int odd) {
+	int i1 = 0, i2 = 1 << (bits - use_par);
+	odd = use_par ? odd : 0;
+	while (i2 - i1 > 1) {
+		const int j = (i1 + i2) / 2;
+		if (v >= (real) expand_bits(bits, (j << use_par) + odd)) i1 = j;
+		else i2 = j;
+	}
+	return (i1 << use_par) + odd;
+}
+
+// index_collapse_ (:513-538); returns the new maximum index
+A7_HD int collapse_indices(int *index, int n) {
+	int mi = index[0], Mi = index[0];
+	for (int k = 1; k < n; k++) {
+		mi = mi < index[k] ? mi : index[k];
+		Mi = Mi > index[k] ? Mi : index[k];
+	}
+	int D = 1;
+	for (int d = 2; d <= Mi - mi; d++) {
+		int k = 0;
+		for (; k < n; k++)
+			if ((index[k] - mi) % d != 0) break;
+		if (k >= n) D = d;
+	}
+	int top = 0;
+	for (int k = 0; k < n; k++) {
+		index[k] = (index[k] - mi) / D;
+		top = top > index[k] ? top : index[k];
+	}
+	return top;
+}
+
+// quant_single_point_d (:546-701): best (endpoints, index) reproducing ONE colour `pt`. Returns per-texel error.
+A7_HD real single_point(const Tables &T, const real pt[4], int clog, const int *bits, int type, int dim, int epo[2][4], int &best_index) {
+	const int use_par = type != 0;
+	const int npv = 1 << type; // npv_nd for types 0..2
+	real err0 = A7_HUGE, err1 = A7_HUGE;
+	int idx = 0, idx1 = 0;
+	int e0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+	for (int pn = 0; pn < npv; pn++) {
+		// parity of endpoint 0 / 1 for this vector (identical across channels for CART / SAME_PAR / BCC)
+		const int par0 = type == SAME_PAR ? pn : (pn >> 1), par1 = type == SAME_PAR ? pn : (pn & 1);
+		const int a0 = use_par ? par0 : 0, a1 = use_par ? par0 + 1 : 2;
+		const int b0 = use_par ? par1 : 0, b1 = use_par ? par1 + 1 : 2;
+		for (int i = 0; i < (1 << clog); i++) {
+			real t = 0;
+			int t1o[4], t2o[4], dr0[4];
+			for (int j = 0; j < dim; j++) {
+				real tbest = A7_HUGE;
+				int tf = (int) floor(pt[j]), tc = (int) ceil(pt[j]);
+				tf = tf < 0 ? 0 : tf;
+				tc = tc > 255 ? 255 : tc;
+				for (int t1 = a0; t1 < a1; t1++)
+					for (int t2 = b0; t2 < b1; t2++) {
+						const uint32_t ef = T.sp[sp_slot(clog, bits[j], tf, t1, t2, i)] >> 16, ec = T.sp[sp_slot(clog, bits[j], tc, t1, t2, i)] >> 16;
+						int dr;
+						if (ef > ec) dr = tc;
+						else if (ef < ec) dr = tf;
+						else dr = (int) floor(pt[j] + 0.5);
+						const real k = (real) (T.sp[sp_slot(clog, bits[j], dr, t1, t2, i)] >> 16);
+						const real tr = k * k + 2 * k * fabs((real) dr - pt[j]) + ((real) dr - pt[j]) * ((real) dr - pt[j]);
+						if (tr < tbest) { tbest = tr; t1o[j] = t1; t2o[j] = t2; dr0[j] = dr; }
+					}
+				t += tbest;
+			}
+			if (t < err0) {
+				idx = i;
+				for (int j = 0; j < dim; j++) {
+					const uint32_t e = T.sp[sp_slot(clog, bits[j], dr0[j], t1o[j], t2o[j], i)];
+					e0[0][j] = (int) (e & 255u);
+					e0[1][j] = (int) ((e >> 8) & 255u);
+				}
+				err0 = t;
+			}
+			if (err0 == 0) break;
+		}
+		if (err0 < err1) {
+			idx1 = idx;
+			for (int j = 0; j < dim; j++) { epo[0][j] = e0[0][j]; epo[1][j] = e0[1][j]; }
+			err1 = err0;
+		}
+		if (err1 == 0) break;
+	}
+	best_index = idx1;
+	return err1;
+}
+
+// Handles the "every texel takes the same index" case shared by both shakers (:789-826, :1114-1140)
+A7_HD real shake_single_index(const Tables &T, const real data[][4], int n, bool all_same, const real mean[4], int clog, const int *bits,
+															int type, int dim, int *index, int epo[2][4]) {
+	int bi;
+	real t;
+	if (all_same) {
+		t = single_point(T, data[0], clog, bits, type, dim, epo, bi) * (real) n;
+	} else {
+		single_point(T, mean, clog, bits, type, dim, epo, bi);
+		t = 0;
+		for (int i = 0; i < n; i++)
+			for (int j = 0; j < dim; j++) {
+				const real o = (real) ramp_int(expand_bits(bits[j], epo[0][j]), expand_bits(bits[j], epo[1][j]), bi, clog);
+				t += (data[i][j] - o) * (data[i][j] - o);
+			}
+	}
+	for (int i = 0; i < n; i++) index[i] = bi;
+	return t;
+}
+
+// Least-squares endpoints for index assignment cidx[] against rounded cluster means (:858-916 == :1160-1219)
+A7_HD void fit_endpoints(const real data[][4], int n, const int *cidx, int Mi_, int dim, real epa[2][4]) {
+	real cc[16][4];
+	int cnt[16];
+	for (int c = 0; c <= Mi_; c++) {
+		cnt[c] = 0;
+		for (int j = 0; j < dim; j++) cc[c][j] = 0;
+	}
+	for (int i = 0; i < n; i++) {
+		for (int j = 0; j < dim; j++) cc[cidx[i]][j] += data[i][j];
+		cnt[cidx[i]]++;
+	}
+	// mean + round of every populated cluster (clusters are independent, so the visit order is irrelevant)
+	for (int c = 0; c <= Mi_; c++)
+		if (cnt[c])
+			for (int j = 0; j < dim; j++) cc[c][j] = floor(cc[c][j] / (real) cnt[c] + 0.5);
+	real im00 = 0, im01 = 0, im11 = 0, rp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+	for (int k = 0; k < n; k++) {
+		const int a = Mi_ - cidx[k], b = cidx[k];
+		im00 += a * a;
+		im01 += b * a;
+		im11 += b * b;
+		for (int j = 0; j < dim; j++) {
+			rp[0][j] += (real) a * cc[b][j];
+			rp[1][j] += (real) b * cc[b][j];
+		}
+	}
+	const real dd = im00 * im11 - im01 * im01;
+	const real i00 = im11 / dd, i11 = im00 / dd, i01 = -im01 / dd;
+	for (int j = 0; j < dim; j++) {
+		epa[0][j] = (i00 * rp[0][j] + i01 * rp[1][j]) * (real) Mi_;
+		epa[1][j] = (i01 * rp[0][j] + i11 * rp[1][j]) * (real) Mi_;
+	}
+}
+
+// ep_shaker_2_d (:703-1053): per-channel window search around the least-squares endpoints with fixed indices,
+// combined over parity vectors, then re-clustering; up to 9 rounds. index[] in/out, epo_code out. Returns SSE.
+A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *index_io, int epo_code[2][4], int size, int Mi_, int bits_total,
+												 int dim) {
+	const int type = bits_total % (2 * dim);
+	const int use_par = type != 0;
+	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
+	int max_bits[4] = {mb, mb, mb, mb};
+	const int clog = ilog2(Mi_ + 1);
+	const int C = 1 << clog;
+	int index[kMaxEntries];
+	for (int k = 0; k < n; k++) index[k] = index_io[k];
+	bool alls = true;
+	for (int i = 1; i < n; i++)
+		for (int j = 0; j < dim; j++) alls = alls && (data[0][j] == data[i][j]);
+	real mean[4] = {0, 0, 0, 0};
+	for (int j = 0; j < dim; j++) {
+		real m = 0;
+		for (int i = 0; i < n; i++) m += data[i][j];
+		mean[j] = m / (real) n;
+	}
+	real err_o = A7_HUGE;
+	int maxTry = 8;
+	int done;
+	do {
+		const int Mi = collapse_indices(index, n);
+		if (Mi == 0) {
+			int e0[2][4];
+			const real t = shake_single_index(T, data, n, alls, mean, clog, max_bits, type, dim, index, e0);
+			if (t < err_o) {
+				for (int k = 0; k < n; k++) index_io[k] = index[k];
+				for (int j = 0; j < dim; j++) { epo_code[0][j] = e0[0][j]; epo_code[1][j] = e0[1][j]; }
+				err_o = t;
+			}
+			return err_o;
+		}
+		int p0 = -1, q0 = -1;
+		real err_0 = A7_HUGE;
+		int epo_0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+		for (int q = 1; q * Mi <= Mi_; q++)
+			for (int p = 0; p <= Mi_ - q * Mi; p++) {
+				int cidx[kMaxEntries];
+				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
+				real epa[2][4];
+				fit_endpoints(data, n, cidx, Mi_, dim, epa);
+				real ed[2][2][4];
+				int ep2[2][2][2][4];
+				const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
+				for (int j = 0; j < dim; j++)
+					for (int pp0 = 0; pp0 < rr; pp0++)
+						for (int pp1 = 0; pp1 < rr; pp1++) {
+							int lo[2], hi[2];
+							for (int i = 0; i < 2; i++) {
+								const int f = endpoint_floor(epa[i][j], mb, use_par, i ? pp1 : pp0);
+								lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
+								hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
+							}
+							real best = A7_HUGE;
+							int b1 = 0, b2 = 0;
+							for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
+								const int e1 = expand_bits(mb, p1);
+								for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
+									const int e2 = expand_bits(mb, p2);
+									real t = 0;
+									for (int m = n - 1; m >= 0; m--) {
+										const real d = (real) ramp_int(e1, e2, cidx[m], clog) - data[m][j];
+										t += d * d;
+									}
+									if (t < best) { best = t; b1 = p1; b2 = p2; }
+								}
+							}
+							ed[pp0][pp1][j] = best;
+							ep2[pp0][pp1][0][j] = b1;
+							ep2[pp0][pp1][1][j] = b2;
+						}
+				real err_1 = A7_HUGE;
+				int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+				for (int pn = 0; pn < (1 << type); pn++) {
+					const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
+					real e2 = 0;
+					for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
+					if (e2 < err_1) {
+						err_1 = e2;
+						for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
+					}
+				}
+				if (err_1 <= err_0) {
+					err_0 = err_1;
+					p0 = p;
+					q0 = q;
+					for (int j = 0; j < dim; j++) { epo_0[0][j] = epo_1[0][j]; epo_0[1][j] = epo_1[1][j]; }
+				}
+			}
+		// re-cluster against the chosen endpoints
+		int e1[4], e2[4];
+		for (int j = 0; j < dim; j++) { e1[j] = expand_bits(mb, epo_0[0][j]); e2[j] = expand_bits(mb, epo_0[1][j]); }
+		int idg[kMaxEntries];
+		real err_r = 0;
+		for (int i = 0; i < n; i++) {
+			real cmin = A7_HUGE;
+			int ci = 0;
+			for (int c = 0; c < C; c++) {
+				real t = 0;
+				for (int k = 0; k < dim; k++) {
+					const real d = (real) ramp_int(e1[k], e2[k], c, clog) - data[i][k];
+					t += d * d;
+				}
+				if (t < cmin) { cmin = t; ci = c; }
+			}
+			idg[i] = ci;
+			err_r += cmin;
+		}
+		int change = 0;
+		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != idg[k]);
+		const int better = err_r < err_o;
+		if (better) {
+			for (int k = 0; k < n; k++) index_io[k] = index[k] = idg[k];
+			for (int j = 0; j < dim; j++) { epo_code[0][j] = epo_0[0][j]; epo_code[1][j] = epo_0[1][j]; }
+			err_o = err_r;
+		}
+		done = !(change && better);
+	} while (!done && maxTry--);
+	return err_o;
+}
+
+// One (odd, flip) lattice of ep_shaker_d (:1230-1353): the 2x2x2 endpoint-neighbour cube of both endpoints walked
+// in the reference's Gray-code order; full re-clustering at each of the 64 corners. Updates (err_1, idx_1) with
+// first-strict-minimum semantics.
+A7_HD void shake_cube_lattice(const real data[][4], int n, int clog, const int *bits, const real epa[2][4], int use_par, int odd, int flip,
+															real &err_1, int *idx_1) {
+	const int C = 1 << clog;
+	int epi[2][3][2];
+	for (int j = 0; j < 3; j++)
+		for (int i = 0; i < 2; i++) {
+			const int f = endpoint_floor(epa[i][j], bits[j], use_par, (odd ^ (flip & i)) & 1);
+			const int top = (1 << bits[j]) - 1;
+			epi[i][j][0] = f;
+			epi[i][j][1] = f + ((top - f < (1 << use_par) ? top - f : (1 << use_par)) & ~use_par);
+		}
+	real r[3][16];
+	for (int j = 0; j < 3; j++) {
+		const int e1 = expand_bits(bits[j], epi[0][j][0]), e2 = expand_bits(bits[j], epi[1][j][0]);
+		for (int c = 0; c < C; c++) r[j][c] = (real) ramp_int(e1, e2, c, clog);
+	}
+	int s = 0;
+	for (int p1 = 0; p1 < 64; p1++) {
+		const int g = p1 & (-p1);
+		int j0 = 0, ei0 = 0, ei1 = 0;
+		for (int j = 0; j < 3; j++)
+			if (((g >> (2 * j)) & 3) != 0) {
+				j0 = j;
+				ei0 = ((s ^ g) >> (2 * j)) & 1;
+				ei1 = ((s ^ g) >> (2 * j + 1)) & 1;
+			}
+		s ^= g;
+		{
+			const int e1 = expand_bits(bits[j0], epi[0][j0][ei0]), e2 = expand_bits(bits[j0], epi[1][j0][ei1]);
+			for (int c = 0; c < C; c++) r[j0][c] = (real) ramp_int(e1, e2, c, clog);
+		}
+		real err_0 = 0;
+		int idx_0[kMaxEntries];
+		for (int i = 0; i < n; i++) {
+			real cmin = A7_HUGE;
+			int ci = 0;
+			for (int c = 0; c < C; c++) {
+				real t = 0;
+				for (int k = 0; k < 3; k++) t += (r[k][c] - data[i][k]) * (r[k][c] - data[i][k]);
+				if (t < cmin) { cmin = t; ci = c; }
+			}
+			idx_0[i] = ci;
+			err_0 += cmin;
+		}
+		if (err_0 < err_1) {
+			for (int i = 0; i < n; i++) idx_1[i] = idx_0[i];
+			err_1 = err_0;
+		}
+	}
+}
+
+// ep_shaker_d (:1058-1404), dimension 3 only (its only use). index[] in/out. Returns SSE.
+A7_HDN real shake_cube(const Tables &T, const real data[][4], int n, int *index_io, int Mi_, const int *bits, int type) {
+	const int dim = 3;
+	const int use_par = (type == BCC || type == SAME_PAR), bcc = (type == BCC);
+	const int clog = ilog2(Mi_ + 1);
+	int index[kMaxEntries];
+	for (int k = 0; k < n; k++) index[k] = index_io[k];
+	bool alls = true;
+	for (int i = 1; i < n; i++)
+		for (int j = 0; j < dim; j++) alls = alls && (data[0][j] == data[i][j]);
+	real mean[4] = {0, 0, 0, 0};
+	for (int j = 0; j < dim; j++) {
+		real m = 0;
+		for (int i = 0; i < n; i++) m += data[i][j];
+		mean[j] = m / (real) n;
+	}
+	real err_o = A7_HUGE;
+	int maxTry = 1, done;
+	do {
+		const int Mi = collapse_indices(index, n);
+		if (Mi == 0) {
+			int e0[2][4];
+			const real t = shake_single_index(T, data, n, alls, mean, clog, bits, type, dim, index, e0);
+			if (t < err_o) {
+				for (int k = 0; k < n; k++) index_io[k] = index[k];
+				err_o = t;
+			}
+			return err_o;
+		}
+		int p0 = -1, q0 = -1;
+		real err_2 = A7_HUGE;
+		int idx_2[kMaxEntries];
+		for (int k = 0; k < n; k++) idx_2[k] = 0;
+		for (int q = 1; q * Mi <= Mi_; q++)
+			for (int p = 0; p <= Mi_ - q * Mi; p++) {
+				int cidx[kMaxEntries];
+				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
+				real epa[2][4];
+				fit_endpoints(data, n, cidx, Mi_, dim, epa);
+				real err_1 = A7_HUGE;
+				int idx_1[kMaxEntries];
+				for (int k = 0; k < n; k++) idx_1[k] = 0;
+				for (int odd = 0; odd <= use_par; odd++)
+					for (int flip = 0; flip <= bcc; flip++) shake_cube_lattice(data, n, clog, bits, epa, use_par, odd, flip, err_1, idx_1);
+				if (err_1 < err_2) {
+					for (int i = 0; i < n; i++) idx_2[i] = idx_1[i];
+					err_2 = err_1;
+					p0 = p;
+					q0 = q;
+				}
+			}
+		int change = 0;
+		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != idx_2[k]);
+		const int better = err_2 < err_o;
+		if (better) {
+			for (int k = 0; k < n; k++) index_io[k] = index[k] = idx_2[k];
+			err_o = err_2;
+		}
+		done = !(change && better);
+	} while (!done && maxTry--);
+	return err_o;
+}
+
+// ---- bit packing -----------------------------------------------------------------------------------------
+struct Bits128 {
+	uint64_t w[2];
+	int pos;
+};
+A7_HD void put_bits(Bits128 &b, uint32_t v, int n) {
+	if (n == 0) return;
+	v &= (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+	const int p = b.pos;
+	if (p < 64) {
+		b.w[0] |= (uint64_t) v << p;
+		if (p + n > 64) b.w[1] |= (uint64_t) v >> (64 - p);
+	} else {
+		b.w[1] |= (uint64_t) v << (p - 64);
+	}
+	b.pos = p + n;
+}
+
+A7_HD int subset_of(int subsets, int partition, int texel) {
+	if (subsets == 2) return (kBc7Part2[partition] >> texel) & 1;
+	if (subsets == 3) return (kBc7Part3[partition] >> (2 * texel)) & 3;
+	return 0;
+}
+
+// Result of one single-index mode: endpoints as integer codes INCLUDING the parity bit in bit 0 (as the shakers
+// produce them), indices per subset in subset-local order.
+struct SingleIndexResult {
+	int partition;
+	int ep[3][2][4];
+	int idx[3][kMaxEntries];
+};
+
+// EncodeSingleIndexBlock (:333-538) + the endpoint packing of :846-881.
+// Reference quirk kept: for ONE_PBIT (mode 1) BOTH p-bits are taken from endpoint 1 of the subset (:443-448), after
+// the anchor flip; the p-bit that endpoint 0 was searched with is dropped.
+A7_HD void pack_single_index(int mode, const SingleIndexResult &r, uint64_t out[2]) {
+	const ModeInfo mi = mode_info(mode);
+	const int dim = mi.alpha == 0 ? 3 : 4;
+	const int cbits = mi.alpha == 0 ? mi.vector_bits / 3 : mi.vector_bits / 4;
+	const int ib = mi.index_bits0;
+	int blk[16], cnt[3] = {0, 0, 0};
+	int fix[3] = {0, 0, 0};
+	if (mi.subsets == 3) { fix[1] = kBc7Anchor3a[r.partition]; fix[2] = kBc7Anchor3b[r.partition]; }
+	else if (mi.subsets == 2) fix[1] = kBc7Anchor2[r.partition];
+	bool flip[3] = {false, false, false};
+	for (int i = 0; i < 16; i++) {
+		const int p = subset_of(mi.subsets, r.partition, i);
+		blk[i] = r.idx[p][cnt[p]++];
+		for (int j = 0; j < mi.subsets; j++)
+			if (i == fix[j] && (blk[i] & (1 << (ib - 1)))) flip[j] = true;
+	}
+	for (int i = 0; i < 16; i++)
+		if (flip[subset_of(mi.subsets, r.partition, i)]) blk[i] = ((1 << ib) - 1) - blk[i];
+	Bits128 b = {{0, 0}, 0};
+	put_bits(b, 1u << mode, mode + 1);
+	put_bits(b, (uint32_t) r.partition, mi.partition_bits);
+	int col[3][2][4], par[3][2];
+	for (int s = 0; s < mi.subsets; s++) {
+		const int a = flip[s] ? 1 : 0;
+		for (int e = 0; e < 2; e++) {
+			const int *src = r.ep[s][e ^ a];
+			par[s][e] = 0;
+			for (int k = 0; k < 4; k++) col[s][e][k] = (mi.parity != CART) ? (src[k] >> 1) : src[k];
+			if (mi.parity != CART) par[s][e] = src[0] & 1;
+		}
+		if (mi.parity == SAME_PAR) par[s][0] = par[s][1]; // ONE_PBIT quirk
+	}
+	for (int k = 0; k < dim; k++)
+		for (int s = 0; s < mi.subsets; s++)
+			for (int e = 0; e < 2; e++) put_bits(b, (uint32_t) col[s][e][k], cbits);
+	if (mi.parity == SAME_PAR)
+		for (int s = 0; s < mi.subsets; s++) put_bits(b, (uint32_t) par[s][0], 1);
+	else if (mi.parity == BCC)
+		for (int s = 0; s < mi.subsets; s++) { put_bits(b, (uint32_t) par[s][0], 1); put_bits(b, (uint32_t) par[s][1], 1); }
+	for (int i = 0; i < 16; i++) {
+		const int p = subset_of(mi.subsets, r.partition, i);
+		put_bits(b, (uint32_t) blk[i], (i == fix[p]) ? ib - 1 : ib);
+	}
+	out[0] = b.w[0];
+	out[1] = b.w[1];
+}
+
+// EncodeDualIndexBlock (:902-1056)
+A7_HD void pack_dual_index(int mode, int index_selection, int rotation, int ep[2][2][4], int idx[2][16], uint64_t out[2]) {
+	const ModeInfo mi = mode_info(mode);
+	Bits128 b = {{0, 0}, 0};
+	put_bits(b, 1u << mode, mode + 1);
+	put_bits(b, (uint32_t) rotation, mi.rotation_bits);
+	put_bits(b, index_selection ? 1u : 0u, mi.index_mode_bits);
+	int ibits[2];
+	ibits[0] = index_selection ? mi.index_bits1 : mi.index_bits0;
+	ibits[1] = index_selection ? mi.index_bits0 : mi.index_bits1;
+	for (int i = 0; i < 2; i++)
+		if (idx[i][0] & (1 << (ibits[i] - 1))) {
+			for (int j = 0; j < 16; j++) idx[i][j] = ((1 << ibits[i]) - 1) - idx[i][j];
+			for (int k = 0; k < 4; k++) { const int t = ep[i][0][k]; ep[i][0][k] = ep[i][1][k]; ep[i][1][k] = t; }
+		}
+	const int vbits = mi.vector_bits / 3;
+	for (int c = 0; c < 4; c++)
+		for (int e = 0; e < 2; e++) {
+			if (c != 3) put_bits(b, (uint32_t) ep[0][e][c], vbits);
+			else put_bits(b, (uint32_t) ep[1][e][0], mi.scalar_bits);
+		}
+	for (int i = 0; i < 2; i++) {
+		const int sel = index_selection ? (i ^ 1) : i;
+		for (int j = 0; j < 16; j++) put_bits(b, (uint32_t) idx[sel][j], j == 0 ? ibits[sel] - 1 : ibits[sel]);
+	}
+	out[0] = b.w[0];
+	out[1] = b.w[1];
+}
+
+// ---- block level (serial orchestration; the CUDA kernel spreads the same tasks over lanes) ---------------
+struct BlockInput {
+	real px[16][4]; // 0..255
+	uint32_t mode_mask; // after the filter of :1340-1380
+};
+
+// CompressBlock's set-up (:1296-1380): scale to 0..255, alpha classification, mode filter
+A7_HD void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInput &B) {
+	bool needs_alpha = false, zero_one = false;
+	real mn[4] = {A7_HUGE, A7_HUGE, A7_HUGE, A7_HUGE}, mx[4] = {0, 0, 0, 0};
+	for (int i = 0; i < 16; i++) {
+		const float a = in[i * 4 + 3];
+		if (a < 1.0) needs_alpha = true;
+		else if (((double) a >= 0.99999) || ((double) a < 0.00001)) zero_one = true;
+		for (int j = 0; j < 4; j++) {
+			const real v = (real) (in[i * 4 + j] * 255.0f);
+			B.px[i][j] = v;
+			mn[j] = v < mn[j] ? v : mn[j];
+			mx[j] = v > mx[j] ? v : mx[j];
+		}
+	}
+	real range = mx[0] - mn[0];
+	for (int j = 1; j < 4; j++) range = range > (mx[j] - mn[j]) ? range : (mx[j] - mn[j]);
+	const bool solid = range < 1e-10;
+	uint32_t mask = valid_mode_mask ? valid_mode_mask : 0xCFu;
+	for (int m = 0; m < 8; m++) {
+		if (!(mask & (1u << m))) continue;
+		const int at = mode_info(m).alpha;
+		if (needs_alpha && at == 0) mask &= ~(1u << m);
+		if (!solid && !needs_alpha && at == 1) mask &= ~(1u << m);
+		if (needs_alpha && zero_one && at == 1) mask &= ~(1u << m);
+	}
+	B.mode_mask = mask;
+}
+
+A7_HD void gather_subset(const BlockInput &B, int subsets, int partition, int subset, int dim, real out[][4], int &n) {
+	n = 0;
+	for (int i = 0; i < 16; i++)
+		if (subset_of(subsets, partition, i) == subset) {
+			for (int j = 0; j < 4; j++) out[n][j] = j < dim ? B.px[i][j] : 0;
+			n++;
+		}
+}
+
+struct ShakeParams {
+	int bits[4]; // per channel incl. parity (0..2), total for both endpoints (3)
+	int shake_size, clusters, dim, parity;
+};
+A7_HD ShakeParams single_index_shake_params(int mode) { // :651-707 at quality 1
+	const ModeInfo mi = mode_info(mode);
+	ShakeParams s;
+	s.dim = mi.alpha == 0 ? 3 : 4;
+	const int cb = mi.alpha == 0 ? mi.vector_bits / 3 : mi.vector_bits / 4;
+	const int par = mi.parity != CART ? 1 : 0;
+	s.bits[0] = s.bits[1] = s.bits[2] = cb + par;
+	s.bits[3] = 2 * cb * s.dim + (mi.parity == BCC ? 2 : (mi.parity == SAME_PAR ? 1 : 0));
+	int ss = 8 - (int) floor(1.5 * mi.index_bits0);
+	ss = ss < 2 ? 2 : (ss > 6 ? 6 : ss);
+	if (par) ss += 2;
+	s.shake_size = ss;
+	s.clusters = 1 << mi.index_bits0;
+	s.parity = mi.parity;
+	return s;
+}
+
+// Shake one subset of one partition (:709-805). idx[] in (quantiser indices) / out. Returns the subset's error.
+A7_HD real shake_subset(const Tables &T, const ShakeParams &sp, const real data[][4], int n, int *idx, int ep[2][4]) {
+	if (sp.dim != 3) return shake_window(T, data, n, idx, ep, sp.shake_size, sp.clusters - 1, sp.bits[3], sp.dim);
+	int tmp[kMaxEntries];
+	for (int k = 0; k < n; k++) tmp[k] = idx[k];
+	const real e0 = shake_cube(T, data, n, tmp, sp.clusters - 1, sp.bits, sp.parity);
+	real e1 = shake_window(T, data, n, idx, ep, sp.shake_size, sp.clusters - 1, sp.bits[3], sp.dim);
+	if (e0 < e1) {
+		e1 = shake_window(T, data, n, tmp, ep, sp.shake_size, sp.clusters - 1, sp.bits[3], sp.dim);
+		for (int k = 0; k < n; k++) idx[k] = tmp[k];
+	}
+	return e1;
+}
+
+// CompressSingleIndexBlock (:548-890)
+A7_HDN real compress_single_index(const Tables &T, const BlockInput &B, int mode, uint64_t out[2]) {
+	const ModeInfo mi = mode_info(mode);
+	const ShakeParams sp = single_index_shake_params(mode);
+	const int nparts = 1 << mi.partition_bits;
+	real perr[64];
+	for (int part = 0; part < nparts; part++) {
+		real e = 0;
+		for (int s = 0; s < mi.subsets; s++) {
+			real sub[kMaxEntries][4];
+			int n, idx[kMaxEntries];
+			gather_subset(B, mi.subsets, part, s, sp.dim, sub, n);
+			if (n) e += quantise_subset(sub, n, sp.clusters, idx, sp.dim);
+		}
+		perr[part] = e;
+	}
+	int order[64];
+	sort_order(perr, order, nparts);
+	const int attempts = nparts < 8 ? nparts : 8;
+	real best = A7_HUGE;
+	SingleIndexResult res, cur;
+	res.partition = 0;
+	for (int a = 0; a < attempts; a++) {
+		const int part = order[a];
+		real e = 0;
+		cur.partition = part;
+		for (int s = 0; s < mi.subsets; s++) {
+			real sub[kMaxEntries][4];
+			int n;
+			gather_subset(B, mi.subsets, part, s, sp.dim, sub, n);
+			if (!n) continue;
+			quantise_subset(sub, n, sp.clusters, cur.idx[s], sp.dim); // the reference stored these in the first pass
+			for (int k = 0; k < 4; k++) cur.ep[s][0][k] = cur.ep[s][1][k] = 0;
+			e += shake_subset(T, sp, sub, n, cur.idx[s], cur.ep[s]);
+		}
+		if (e < best) { best = e; res = cur; }
+	}
+	pack_single_index(mode, res, out);
+	return best;
+}
+
+// CompressDualIndexBlock (:1059-1278) at quality 1: every rotation x index selection is quantised and shaken
+A7_HD int rotation_channel(int rotation, int slot) { // componentRotations (:894-900)
+	const int t[4][4] = {{3, 0, 1, 2}, {0, 3, 1, 2}, {1, 0, 3, 2}, {2, 0, 1, 3}};
+	return t[rotation][slot];
+}
+struct DualCombo {
+	real err;
+	int ep[2][2][4];
+	int idx[2][16];
+};
+A7_HD void dual_index_combo(const Tables &T, const BlockInput &B, int mode, int rotation, int isel, DualCombo &r) {
+	const ModeInfo mi = mode_info(mode);
+	real cb[16][4], ab[16][4];
+	for (int i = 0; i < 16; i++) {
+		cb[i][0] = B.px[i][rotation_channel(rotation, 1)];
+		cb[i][1] = B.px[i][rotation_channel(rotation, 2)];
+		cb[i][2] = B.px[i][rotation_channel(rotation, 3)];
+		cb[i][3] = 0;
+		ab[i][0] = ab[i][1] = ab[i][2] = B.px[i][rotation_channel(rotation, 0)];
+		ab[i][3] = 0;
+	}
+	const int ib[2] = {mi.index_bits0, mi.index_bits1};
+	const int vb = mi.vector_bits / 3, sb = mi.scalar_bits;
+	quantise_subset(cb, 16, 1 << ib[isel], r.idx[0], 3);
+	quantise_subset(ab, 16, 1 << ib[1 ^ isel], r.idx[1], 3);
+	const int bits0[4] = {vb, vb, vb, 6 * vb}, bits1[4] = {sb, sb, sb, 6 * sb};
+	for (int i = 0; i < 2; i++)
+		for (int e = 0; e < 2; e++)
+			for (int k = 0; k < 4; k++) r.ep[i][e][k] = 0;
+	real e = 0;
+	shake_cube(T, cb, 16, r.idx[0], (1 << ib[isel]) - 1, bits0, CART);
+	e += shake_window(T, cb, 16, r.idx[0], r.ep[0], 6, (1 << ib[isel]) - 1, bits0[3], 3);
+	shake_cube(T, ab, 16, r.idx[1], (1 << ib[1 ^ isel]) - 1, bits1, CART);
+	e += shake_window(T, ab, 16, r.idx[1], r.ep[1], 6, (1 << ib[1 ^ isel]) - 1, bits1[3], 3) / 3.;
+	r.err = e;
+}
+A7_HDN real compress_dual_index(const Tables &T, const BlockInput &B, int mode, uint64_t out[2]) {
+	const ModeInfo mi = mode_info(mode);
+	real best = A7_HUGE;
+	for (int rot = 0; rot < (1 << mi.rotation_bits); rot++)
+		for (int isel = 0; isel < (1 << mi.index_mode_bits); isel++) {
+			DualCombo c;
+			dual_index_combo(T, B, mode, rot, isel, c);
+			if (c.err < best) {
+				pack_dual_index(mode, isel, rot, c.ep, c.idx, out);
+				best = c.err;
+			}
+		}
+	return best;
+}
+
+// CompressBlock (:1289-1465): modes in the order {6,4,3,1,2,0,7,5}, first strict minimum wins
+A7_HD int mode_visit_order(int i) { return (int) ((0x57021346u >> (4 * i)) & 15u); }
+A7_HD real encode_block_serial(const Tables &T, const float in[64], uint32_t valid_mode_mask, uint64_t out[2]) {
+	BlockInput B;
+	prepare_block(in, valid_mode_mask, B);
+	real best = A7_HUGE;
+	out[0] = out[1] = 0;
+	for (int i = 0; i < 8; i++) {
+		const int m = mode_visit_order(i);
+		if (!(B.mode_mask & (1u << m))) continue;
+		uint64_t tmp[2];
+		const real e = (mode_info(m).alpha != 2) ? compress_single_index(T, B, m, tmp) : compress_dual_index(T, B, m, tmp);
+		if (e < best) { best = e; out[0] = tmp[0]; out[1] = tmp[1]; }
+	}
+	return best;
+}
+
+} // namespace amd7
+} // namespace b200ic

@@ -7,7 +7,40 @@
 #include "bc7rg_core.cuh"
 #endif
 
+#ifdef HB_BC7AMD
+#include "bc7amd_core.cuh"
+#include <thread>
+#include <vector>
+#include <atomic>
+#endif
+
 extern "C" {
+#ifdef HB_BC7AMD
+static uint32_t *hb_sp_table() {
+	static std::vector<uint32_t> sp;
+	if (sp.empty()) { sp.resize(b200ic::amd7::kSpEntries); b200ic::amd7::build_single_point_table(sp.data()); }
+	return sp.data();
+}
+// in: nblocks x 64 floats (RGBA 0..1, texel order); out: nblocks x 16 bytes; err (may be NULL): encoder's SSE per block
+void hb_bc7amd_blocks(const float *in, uint64_t nblocks, uint32_t mode_mask, uint8_t *out, double *err, int nthreads) {
+	b200ic::amd7::Tables T{hb_sp_table()};
+	std::atomic<uint64_t> next{0};
+	auto work = [&]() {
+		for (;;) {
+			const uint64_t b = next.fetch_add(1);
+			if (b >= nblocks) break;
+			uint64_t w[2];
+			const double e = b200ic::amd7::encode_block_serial(T, in + b * 64, mode_mask, w);
+			memcpy(out + b * 16, w, 16);
+			if (err) err[b] = e;
+		}
+	};
+	if (nthreads <= 1) { work(); return; }
+	std::vector<std::thread> pool;
+	for (int t = 0; t < nthreads; t++) pool.emplace_back(work);
+	for (auto &t : pool) t.join();
+}
+#endif
 #ifdef HB_BC7RG
 void hb_bc7rg_blocks(const uint32_t *px, uint64_t nblocks, int perceptual, int fast, uint8_t *out) {
 	static b200ic::rg::OptimalEndpoint table[512];
