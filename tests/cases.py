@@ -74,3 +74,9 @@ def rgba_cases(small: bool = False):
     lowc = (rng.integers(0, 6, (n // 2, n // 2, 4)) + np.array([120, 60, 200, 250])).astype(np.uint8)
     out.append(("low_contrast", lowc, synth.FMT_RGBA8))
     return out
+
+
+def to_blocks_f32(img: np.ndarray) -> np.ndarray:
+    """(H, W, 4) uint8 -> (nblocks, 64) float32 exactly as the shim's Image_GetPixelAtF decodes (x / 255.0f)."""
+    u = to_blocks_rgba8(np.ascontiguousarray(img)).view(np.uint8).reshape(-1, 16, 4)
+    return np.ascontiguousarray((u.astype(np.float32) / np.float32(255)).reshape(-1, 64))
