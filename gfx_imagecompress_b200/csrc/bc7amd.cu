@@ -14,7 +14,7 @@
 // to the reference's wherever its qsort tie order does not matter.
 #include "common.cuh"
 #include "kernels.h"
-#include "bc7amd_core.cuh"
+#include "bc7amd_block.cuh"
 
 namespace b200ic {
 
@@ -61,6 +61,7 @@ __device__ __forceinline__ uint32_t pack_ep(const int e[4]) {
 	return (uint32_t) (e[0] & 255) | ((uint32_t) (e[1] & 255) << 8) | ((uint32_t) (e[2] & 255) << 16) | ((uint32_t) (e[3] & 255) << 24);
 }
 
+template <bool U8>
 __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) {
 	__shared__ WarpScratch scratch[kWarps];
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -126,7 +127,13 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 				o.err = 0; o.idx = 0; o.ep[0] = o.ep[1] = 0;
 				if (n) {
 					quantise_subset(sub, n, sp.clusters, idx, sp.dim);
-					o.err = shake_subset(T, sp, sub, n, idx, ep);
+					if (U8) {
+						U8Subset S;
+						make_u8_subset(sub, n, sp.dim, S);
+						o.err = shake_subset_u8(T, sp, S, idx, ep);
+					} else {
+						o.err = shake_subset(T, sp, sub, n, idx, ep);
+					}
 					o.idx = pack_idx(idx, n);
 					o.ep[0] = pack_ep(ep[0]);
 					o.ep[1] = pack_ep(ep[1]);
@@ -181,9 +188,16 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 				const int bits[4] = {cb, cb, cb, 6 * cb};
 				int idx[16], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 				quantise_subset(blkv, 16, 1 << ib, idx, 3);
-				shake_cube(T, blkv, 16, idx, (1 << ib) - 1, bits, CART);
 				ShakeOut o;
-				o.err = shake_window(T, blkv, 16, idx, ep, 6, (1 << ib) - 1, bits[3], 3);
+				if (U8) {
+					U8Subset S;
+					make_u8_subset(blkv, 16, 3, S);
+					shake_cube_u8_any(T, S, idx, ib, bits, CART);
+					o.err = shake_window_u8_any(T, S, idx, ep, 6, ib, bits[3], 3);
+				} else {
+					shake_cube(T, blkv, 16, idx, (1 << ib) - 1, bits, CART);
+					o.err = shake_window(T, blkv, 16, idx, ep, 6, (1 << ib) - 1, bits[3], 3);
+				}
 				o.idx = pack_idx(idx, 16);
 				o.ep[0] = pack_ep(ep[0]);
 				o.ep[1] = pack_ep(ep[1]);
@@ -262,7 +276,12 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	p.mode_mask = (uint32_t) opts.amd_mode_mask & 0xffu;
 	if (p.n_blocks == 0) return cudaSuccess;
 	const uint64_t grid = (p.n_blocks + kWarps - 1) / kWarps;
-	bc7amd_kernel<<<(unsigned) grid, kWarps * 32, 0, stream>>>(p);
+	// 8-bit sources: every component is an exact integer, the exact INT32 shakers apply (bc7amd_int.cuh)
+	const bool u8 = img.format == B200IC_FMT_R8 || img.format == B200IC_FMT_RG8 || img.format == B200IC_FMT_RGB8 ||
+									img.format == B200IC_FMT_RGB8_SRGB || img.format == B200IC_FMT_RGBA8 || img.format == B200IC_FMT_RGBA8_SRGB ||
+									img.format == B200IC_FMT_BLOCKS_RGBA8;
+	if (u8) bc7amd_kernel<true><<<(unsigned) grid, kWarps * 32, 0, stream>>>(p);
+	else bc7amd_kernel<false><<<(unsigned) grid, kWarps * 32, 0, stream>>>(p);
 	return cudaGetLastError();
 }
 

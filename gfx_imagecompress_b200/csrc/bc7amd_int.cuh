@@ -1,0 +1,404 @@
+// bc7amd_int.cuh -- exact integer forms of the AMD BC7 endpoint shakers for 8-bit sources.
+//
+// For R8/RG8/RGB8/RGBA8 sources every texel component the encoder sees is an exact integer 0..255
+// ((x / 255.0f) * 255.0f == x for all 256 x), and every ramp value is an integer, so the error sums of
+// ep_shaker_d / ep_shaker_2_d (reference src/amd_shake.cpp:703-1404) are integers below 2^22: INT32 arithmetic gives
+// the reference's FP64 results EXACTLY, in any summation order.  That turns the reference's hottest loop (82 % of its
+// CPU time) into four native sm_100a instructions per (texel, ramp entry) for all channels at once:
+//     VABSDIFF4.U8 (|palette - texel| per byte), IDP.4A.U8.U8 (sum of squares), LEA (error<<4 | entry), VIMNMX.U32
+// and "first strict minimum in scan order" becomes a plain unsigned min of (error, scan position) keys.
+// The least-squares endpoint fit, the floor search on the endpoint lattice and the single-colour path keep the
+// reference's FP64 operations (their inputs are exact integers, so they reproduce it bit for bit as well).
+// The functions are drop-in equivalents of shake_cube / shake_window in bc7amd_core.cuh (tests/hostbuild checks
+// them against those and against the compiled reference).
+#pragma once
+#include "bc7amd_core.cuh"
+
+namespace b200ic {
+namespace amd7 {
+
+A7_HD uint32_t sq_dist4(uint32_t a, uint32_t b) { // sum over the 4 bytes of (a_k - b_k)^2
+#if defined(__CUDA_ARCH__)
+	const uint32_t ad = __vabsdiffu4(a, b);
+	return __dp4a(ad, ad, 0u);
+#else
+	uint32_t t = 0;
+	for (int k = 0; k < 4; k++) {
+		const int d = (int) ((a >> (8 * k)) & 255u) - (int) ((b >> (8 * k)) & 255u);
+		t += (uint32_t) (d * d);
+	}
+	return t;
+#endif
+}
+A7_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+A7_HD uint32_t byte_of(uint64_t v, int i) { return (uint32_t) (v >> (8 * i)) & 255u; }
+
+// ramp values of all C entries between two EXPANDED endpoints, one byte each (C <= 8 fits a u64; C = 16 uses two)
+template <int CLOG> A7_HD void ramp_bytes(int e1, int e2, uint64_t out[(1 << CLOG) > 8 ? 2 : 1]) {
+	constexpr int C = 1 << CLOG, D = C - 1;
+	int num = 2 * D * e1 + D;
+	const int step = 2 * (e2 - e1);
+	out[0] = 0;
+	if (C > 8) out[1] = 0;
+#pragma unroll
+	for (int c = 0; c < C; c++) {
+		const uint32_t v = (uint32_t) (num / (2 * D));
+		if (c < 8) out[0] |= (uint64_t) v << (8 * c);
+		else out[1] |= (uint64_t) v << (8 * (c - 8));
+		num += step;
+	}
+}
+
+struct ClusterStats {
+	int cnt[16];
+	int sum[16][4];
+};
+// per-cluster counts and channel sums of packed texels d[] under index assignment cidx[]
+A7_HD void cluster_stats(const uint32_t *d, int n, const int *cidx, int Mi_, int dim, ClusterStats &cs) {
+	for (int c = 0; c <= Mi_; c++) {
+		cs.cnt[c] = 0;
+		for (int j = 0; j < 4; j++) cs.sum[c][j] = 0;
+	}
+	for (int i = 0; i < n; i++) {
+		const int c = cidx[i];
+		cs.cnt[c]++;
+		for (int j = 0; j < dim; j++) cs.sum[c][j] += (int) ((d[i] >> (8 * j)) & 255u);
+	}
+}
+// fit_endpoints on exact-integer data (same FP64 operations as the reference; sums of integers are exact)
+A7_HD void fit_endpoints_u8(const ClusterStats &cs, const int *cidx, int n, int Mi_, int dim, real epa[2][4]) {
+	real cc[16][4];
+	for (int c = 0; c <= Mi_; c++)
+		if (cs.cnt[c])
+			for (int j = 0; j < dim; j++) cc[c][j] = floor((real) cs.sum[c][j] / (real) cs.cnt[c] + 0.5);
+	real im00 = 0, im01 = 0, im11 = 0, rp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+	for (int k = 0; k < n; k++) {
+		const int a = Mi_ - cidx[k], b = cidx[k];
+		im00 += a * a;
+		im01 += b * a;
+		im11 += b * b;
+		for (int j = 0; j < dim; j++) {
+			rp[0][j] += (real) a * cc[b][j];
+			rp[1][j] += (real) b * cc[b][j];
+		}
+	}
+	const real dd = im00 * im11 - im01 * im01;
+	const real i00 = im11 / dd, i11 = im00 / dd, i01 = -im01 / dd;
+	for (int j = 0; j < dim; j++) {
+		epa[0][j] = (i00 * rp[0][j] + i01 * rp[1][j]) * (real) Mi_;
+		epa[1][j] = (i01 * rp[0][j] + i11 * rp[1][j]) * (real) Mi_;
+	}
+}
+
+struct U8Subset {
+	uint32_t d[kMaxEntries]; // packed texels, channel j in byte j (unused channels 0)
+	int n;
+	bool all_same;
+	real mean[4];
+};
+A7_HD void make_u8_subset(const real data[][4], int n, int dim, U8Subset &S) {
+	S.n = n;
+	int sum[4] = {0, 0, 0, 0};
+	bool same = true;
+	for (int i = 0; i < n; i++) {
+		uint32_t v = 0;
+		for (int j = 0; j < dim; j++) {
+			const int b = (int) data[i][j];
+			v |= (uint32_t) b << (8 * j);
+			sum[j] += b;
+		}
+		S.d[i] = v;
+		same = same && (v == S.d[0]);
+	}
+	S.all_same = same;
+	for (int j = 0; j < 4; j++) S.mean[j] = j < dim ? (real) sum[j] / (real) n : 0;
+}
+
+// the Mi == 0 path of both shakers on packed data (see shake_single_index)
+A7_HD real shake_single_index_u8(const Tables &T, const U8Subset &S, int clog, const int *bits, int type, int dim, int *index, int epo[2][4]) {
+	int bi;
+	real t;
+	if (S.all_same) {
+		real pt[4];
+		for (int j = 0; j < 4; j++) pt[j] = (real) ((S.d[0] >> (8 * j)) & 255u);
+		t = single_point(T, pt, clog, bits, type, dim, epo, bi) * (real) S.n;
+	} else {
+		single_point(T, S.mean, clog, bits, type, dim, epo, bi);
+		uint32_t o = 0;
+		for (int j = 0; j < dim; j++) o |= (uint32_t) ramp_int(expand_bits(bits[j], epo[0][j]), expand_bits(bits[j], epo[1][j]), bi, clog) << (8 * j);
+		uint32_t e = 0;
+		for (int i = 0; i < S.n; i++) e += sq_dist4(S.d[i], o);
+		t = (real) e;
+	}
+	for (int i = 0; i < S.n; i++) index[i] = bi;
+	return t;
+}
+
+A7_HD int gray_position(int s) { // p1 with gray(p1) == s, 6 bits
+	s ^= s >> 1;
+	s ^= s >> 2;
+	s ^= s >> 4;
+	return s & 63;
+}
+
+// All lattices of ep_shaker_d for one (q, p): returns min over (lattice, corner) of err << 8 | lattice << 6 | gray position,
+// and that corner's index assignment (4 bits per texel).
+template <int CLOG>
+A7_HD void cube_search_u8(const U8Subset &S, const int *bits, const real epa[2][4], int use_par, int bcc, uint32_t &best_key, uint64_t &best_idx) {
+	constexpr int C = 1 << CLOG;
+	// floor of each ideal endpoint on the parity-0 and parity-1 lattice
+	int fl[2][3][2];
+	for (int e = 0; e < 2; e++)
+		for (int k = 0; k < 3; k++)
+			for (int par = 0; par <= use_par; par++) fl[e][k][par] = endpoint_floor(epa[e][k], bits[k], use_par, par);
+	int lattice = 0;
+	for (int odd = 0; odd <= use_par; odd++)
+		for (int flip = 0; flip <= bcc; flip++, lattice++) {
+			uint64_t tab[3][4]; // [channel][ei0 + 2*ei1] -> C ramp bytes
+			for (int k = 0; k < 3; k++) {
+				int ep[2][2];
+				for (int e = 0; e < 2; e++) {
+					const int f = fl[e][k][(odd ^ (flip & e)) & 1];
+					const int top = (1 << bits[k]) - 1;
+					ep[e][0] = expand_bits(bits[k], f);
+					ep[e][1] = expand_bits(bits[k], f + ((top - f < (1 << use_par) ? top - f : (1 << use_par)) & ~use_par));
+				}
+				for (int x = 0; x < 4; x++) ramp_bytes<CLOG>(ep[0][x & 1], ep[1][x >> 1], &tab[k][x]);
+			}
+			for (int z = 0; z < 4; z++)
+				for (int y = 0; y < 4; y++) {
+					uint32_t pzy[C];
+#pragma unroll
+					for (int c = 0; c < C; c++) pzy[c] = (byte_of(tab[2][z], c) << 16) | (byte_of(tab[1][y], c) << 8);
+#pragma unroll
+					for (int x = 0; x < 4; x++) {
+						uint32_t pal[C];
+#pragma unroll
+						for (int c = 0; c < C; c++) pal[c] = pzy[c] | byte_of(tab[0][x], c);
+						uint32_t err = 0;
+						uint64_t idx = 0;
+						for (int i = 0; i < S.n; i++) {
+							const uint32_t d = S.d[i];
+							uint32_t m = 0xffffffffu;
+#pragma unroll
+							for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], d) << 4) | (uint32_t) c);
+							err += m >> 4;
+							idx |= (uint64_t) (m & 15u) << (4 * i);
+						}
+						const uint32_t key = (err << 8) | ((uint32_t) lattice << 6) | (uint32_t) gray_position(x | (y << 2) | (z << 4));
+						if (key < best_key) { best_key = key; best_idx = idx; }
+					}
+				}
+		}
+}
+
+// ep_shaker_d on packed 8-bit data (dimension 3). index_io in/out; returns the SSE (exact integer as real).
+template <int CLOG>
+A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, const int *bits, int type) {
+	constexpr int Mi_ = (1 << CLOG) - 1;
+	const int n = S.n;
+	const int use_par = (type == BCC || type == SAME_PAR), bcc = (type == BCC);
+	int index[kMaxEntries];
+	for (int k = 0; k < n; k++) index[k] = index_io[k];
+	real err_o = A7_HUGE;
+	int maxTry = 1, done;
+	do {
+		const int Mi = collapse_indices(index, n);
+		if (Mi == 0) {
+			int e0[2][4];
+			const real t = shake_single_index_u8(T, S, CLOG, bits, type, 3, index, e0);
+			if (t < err_o) {
+				for (int k = 0; k < n; k++) index_io[k] = index[k];
+				err_o = t;
+			}
+			return err_o;
+		}
+		int p0 = -1, q0 = -1;
+		uint32_t err_2 = 0xffffffffu;
+		uint64_t idx_2 = 0;
+		for (int q = 1; q * Mi <= Mi_; q++)
+			for (int p = 0; p <= Mi_ - q * Mi; p++) {
+				int cidx[kMaxEntries];
+				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
+				ClusterStats cs;
+				cluster_stats(S.d, n, cidx, Mi_, 3, cs);
+				real epa[2][4];
+				fit_endpoints_u8(cs, cidx, n, Mi_, 3, epa);
+				uint32_t key = 0xffffffffu;
+				uint64_t idx_1 = 0;
+				cube_search_u8<CLOG>(S, bits, epa, use_par, bcc, key, idx_1);
+				const uint32_t err_1 = key >> 8;
+				if (err_1 < err_2) {
+					err_2 = err_1;
+					idx_2 = idx_1;
+					p0 = p;
+					q0 = q;
+				}
+			}
+		int change = 0;
+		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != (int) ((idx_2 >> (4 * k)) & 15u));
+		const int better = (real) err_2 < err_o;
+		if (better) {
+			for (int k = 0; k < n; k++) index_io[k] = index[k] = (int) ((idx_2 >> (4 * k)) & 15u);
+			err_o = (real) err_2;
+		}
+		done = !(change && better);
+	} while (!done && maxTry--);
+	return err_o;
+}
+
+// ep_shaker_2_d on packed 8-bit data (dimension 3 or 4). index_io in/out, epo_code out; returns the SSE.
+template <int CLOG>
+A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, int epo_code[2][4], int size, int bits_total, int dim) {
+	constexpr int C = 1 << CLOG, Mi_ = C - 1;
+	constexpr int W = C > 8 ? 2 : 1;
+	const int n = S.n;
+	const int type = bits_total % (2 * dim);
+	const int use_par = type != 0;
+	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
+	const int max_bits[4] = {mb, mb, mb, mb};
+	int index[kMaxEntries];
+	for (int k = 0; k < n; k++) index[k] = index_io[k];
+	int sq_total[4] = {0, 0, 0, 0}; // sum of squares of the data per channel
+	for (int i = 0; i < n; i++)
+		for (int j = 0; j < dim; j++) {
+			const int b = (int) ((S.d[i] >> (8 * j)) & 255u);
+			sq_total[j] += b * b;
+		}
+	real err_o = A7_HUGE;
+	int maxTry = 8, done;
+	do {
+		const int Mi = collapse_indices(index, n);
+		if (Mi == 0) {
+			int e0[2][4];
+			const real t = shake_single_index_u8(T, S, CLOG, max_bits, type, dim, index, e0);
+			if (t < err_o) {
+				for (int k = 0; k < n; k++) index_io[k] = index[k];
+				for (int j = 0; j < dim; j++) { epo_code[0][j] = e0[0][j]; epo_code[1][j] = e0[1][j]; }
+				err_o = t;
+			}
+			return err_o;
+		}
+		int p0 = -1, q0 = -1;
+		int64_t err_0 = INT64_MAX;
+		int epo_0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+		for (int q = 1; q * Mi <= Mi_; q++)
+			for (int p = 0; p <= Mi_ - q * Mi; p++) {
+				int cidx[kMaxEntries];
+				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
+				ClusterStats cs;
+				cluster_stats(S.d, n, cidx, Mi_, dim, cs);
+				real epa[2][4];
+				fit_endpoints_u8(cs, cidx, n, Mi_, dim, epa);
+				int ed[2][2][4], ep2[2][2][2][4];
+				const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
+				for (int j = 0; j < dim; j++)
+					for (int pp0 = 0; pp0 < rr; pp0++)
+						for (int pp1 = 0; pp1 < rr; pp1++) {
+							int lo[2], hi[2];
+							for (int i = 0; i < 2; i++) {
+								const int f = endpoint_floor(epa[i][j], mb, use_par, i ? pp1 : pp0);
+								lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
+								hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
+							}
+							int best = INT32_MAX, b1 = 0, b2 = 0;
+							for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
+								const int e1 = expand_bits(mb, p1);
+								for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
+									uint64_t rv[W];
+									ramp_bytes<CLOG>(e1, expand_bits(mb, p2), rv);
+									// sum_m (rv[cidx[m]] - d[m])^2 == sum d^2 + sum_c rv_c * (cnt_c * rv_c - 2 * S1_c)
+									int t = sq_total[j];
+#pragma unroll
+									for (int c = 0; c < C; c++) {
+										const int r = (int) byte_of(rv[c >> 3], c & 7);
+										t += r * (cs.cnt[c] * r - 2 * cs.sum[c][j]);
+									}
+									if (t < best) { best = t; b1 = p1; b2 = p2; }
+								}
+							}
+							ed[pp0][pp1][j] = best;
+							ep2[pp0][pp1][0][j] = b1;
+							ep2[pp0][pp1][1][j] = b2;
+						}
+				int64_t err_1 = INT64_MAX;
+				int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+				for (int pn = 0; pn < (1 << type); pn++) {
+					const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
+					int64_t e2 = 0;
+					for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
+					if (e2 < err_1) {
+						err_1 = e2;
+						for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
+					}
+				}
+				if (err_1 <= err_0) {
+					err_0 = err_1;
+					p0 = p;
+					q0 = q;
+					for (int j = 0; j < dim; j++) { epo_0[0][j] = epo_1[0][j]; epo_0[1][j] = epo_1[1][j]; }
+				}
+			}
+		// re-cluster against the chosen endpoints: packed palette, 4 native instructions per (texel, entry)
+		uint32_t pal[C];
+		{
+			uint64_t rb[4][W];
+			for (int j = 0; j < 4; j++) {
+				rb[j][0] = 0;
+				if (W > 1) rb[j][W - 1] = 0;
+				if (j < dim) ramp_bytes<CLOG>(expand_bits(mb, epo_0[0][j]), expand_bits(mb, epo_0[1][j]), rb[j]);
+			}
+#pragma unroll
+			for (int c = 0; c < C; c++)
+				pal[c] = byte_of(rb[0][c >> 3], c & 7) | (byte_of(rb[1][c >> 3], c & 7) << 8) | (byte_of(rb[2][c >> 3], c & 7) << 16) |
+								 (byte_of(rb[3][c >> 3], c & 7) << 24);
+		}
+		uint32_t err_r = 0;
+		uint64_t idg = 0;
+		for (int i = 0; i < n; i++) {
+			uint32_t m = 0xffffffffu;
+#pragma unroll
+			for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], S.d[i]) << 4) | (uint32_t) c);
+			err_r += m >> 4;
+			idg |= (uint64_t) (m & 15u) << (4 * i);
+		}
+		int change = 0;
+		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != (int) ((idg >> (4 * k)) & 15u));
+		const int better = (real) err_r < err_o;
+		if (better) {
+			for (int k = 0; k < n; k++) index_io[k] = index[k] = (int) ((idg >> (4 * k)) & 15u);
+			for (int j = 0; j < dim; j++) { epo_code[0][j] = epo_0[0][j]; epo_code[1][j] = epo_0[1][j]; }
+			err_o = (real) err_r;
+		}
+		done = !(change && better);
+	} while (!done && maxTry--);
+	return err_o;
+}
+
+// runtime-CLOG front ends
+A7_HD real shake_cube_u8_any(const Tables &T, const U8Subset &S, int *idx, int clog, const int *bits, int type) {
+	return clog == 2 ? shake_cube_u8<2>(T, S, idx, bits, type) : shake_cube_u8<3>(T, S, idx, bits, type);
+}
+A7_HD real shake_window_u8_any(const Tables &T, const U8Subset &S, int *idx, int ep[2][4], int size, int clog, int bits_total, int dim) {
+	if (clog == 2) return shake_window_u8<2>(T, S, idx, ep, size, bits_total, dim);
+	if (clog == 3) return shake_window_u8<3>(T, S, idx, ep, size, bits_total, dim);
+	return shake_window_u8<4>(T, S, idx, ep, size, bits_total, dim);
+}
+
+// shake_subset (bc7amd_core.cuh) on packed data
+A7_HD real shake_subset_u8(const Tables &T, const ShakeParams &sp, const U8Subset &S, int *idx, int ep[2][4]) {
+	const int clog = ilog2(sp.clusters);
+	if (sp.dim != 3) return shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], sp.dim);
+	int tmp[kMaxEntries];
+	for (int k = 0; k < S.n; k++) tmp[k] = idx[k];
+	const real e0 = shake_cube_u8_any(T, S, tmp, clog, sp.bits, sp.parity);
+	real e1 = shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], sp.dim);
+	if (e0 < e1) {
+		e1 = shake_window_u8_any(T, S, tmp, ep, sp.shake_size, clog, sp.bits[3], sp.dim);
+		for (int k = 0; k < S.n; k++) idx[k] = tmp[k];
+	}
+	return e1;
+}
+
+} // namespace amd7
+} // namespace b200ic

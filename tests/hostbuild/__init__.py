@@ -35,16 +35,16 @@ def load():
     L = C.CDLL(_LIB)
     L.hb_bc7rg_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
     if hasattr(L, "hb_bc7amd_blocks"):
-        L.hb_bc7amd_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        L.hb_bc7amd_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return L
 
 
-def bc7amd_blocks(L, blocks_f32: np.ndarray, mode_mask: int = 0xFF, threads: int = 8):
+def bc7amd_blocks(L, blocks_f32: np.ndarray, mode_mask: int = 0xFF, threads: int = 8, u8_path: bool = False):
     """blocks_f32: (N, 64) float32 RGBA 0..1 in texel order. Returns (blocks uint8 (N,16), encoder SSE (N,))."""
     b = np.ascontiguousarray(blocks_f32, np.float32).reshape(-1, 64)
     out = np.zeros((len(b), 16), np.uint8)
     err = np.zeros(len(b), np.float64)
-    L.hb_bc7amd_blocks(b.ctypes.data, len(b), mode_mask, out.ctypes.data, err.ctypes.data, threads)
+    L.hb_bc7amd_blocks(b.ctypes.data, len(b), mode_mask, out.ctypes.data, err.ctypes.data, threads, int(u8_path))
     return out, err
 
 

@@ -8,7 +8,7 @@
 #endif
 
 #ifdef HB_BC7AMD
-#include "bc7amd_core.cuh"
+#include "bc7amd_block.cuh"
 #include <thread>
 #include <vector>
 #include <atomic>
@@ -22,7 +22,7 @@ static uint32_t *hb_sp_table() {
 	return sp.data();
 }
 // in: nblocks x 64 floats (RGBA 0..1, texel order); out: nblocks x 16 bytes; err (may be NULL): encoder's SSE per block
-void hb_bc7amd_blocks(const float *in, uint64_t nblocks, uint32_t mode_mask, uint8_t *out, double *err, int nthreads) {
+void hb_bc7amd_blocks(const float *in, uint64_t nblocks, uint32_t mode_mask, uint8_t *out, double *err, int nthreads, int u8_path) {
 	b200ic::amd7::Tables T{hb_sp_table()};
 	std::atomic<uint64_t> next{0};
 	auto work = [&]() {
@@ -30,7 +30,8 @@ void hb_bc7amd_blocks(const float *in, uint64_t nblocks, uint32_t mode_mask, uin
 			const uint64_t b = next.fetch_add(1);
 			if (b >= nblocks) break;
 			uint64_t w[2];
-			const double e = b200ic::amd7::encode_block_serial(T, in + b * 64, mode_mask, w);
+			const double e = u8_path ? b200ic::amd7::encode_block_serial<true>(T, in + b * 64, mode_mask, w)
+			                         : b200ic::amd7::encode_block_serial<false>(T, in + b * 64, mode_mask, w);
 			memcpy(out + b * 16, w, 16);
 			if (err) err[b] = e;
 		}
