@@ -34,6 +34,8 @@ def load():
                        ["-I" + _CSRC, "-I" + os.path.join(_ROOT, "include"), "-o", _LIB, os.path.join(_HERE, "hostbuild.cpp")], check=True)
     L = C.CDLL(_LIB)
     L.hb_bc7rg_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    if hasattr(L, "hb_bc1_blocks"):
+        L.hb_bc1_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
     if hasattr(L, "hb_bc7amd_blocks"):
         L.hb_bc7amd_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return L
@@ -52,4 +54,11 @@ def bc7rg_blocks(L, blocks_u32: np.ndarray, perceptual=True, fast=False) -> np.n
     b = np.ascontiguousarray(blocks_u32, np.uint32).reshape(-1, 16)
     out = np.zeros((len(b), 16), np.uint8)
     L.hb_bc7rg_blocks(b.ctypes.data, len(b), int(perceptual), int(fast), out.ctypes.data)
+    return out
+
+
+def bc1_blocks(L, blocks_f32: np.ndarray, alpha_threshold: float = 128 / 255.0, steps: int = 1) -> np.ndarray:
+    b = np.ascontiguousarray(blocks_f32, np.float32).reshape(-1, 64)
+    out = np.zeros((len(b), 8), np.uint8)
+    L.hb_bc1_blocks(b.ctypes.data, len(b), alpha_threshold, steps, out.ctypes.data)
     return out

@@ -14,7 +14,21 @@
 #include <atomic>
 #endif
 
+#ifdef HB_BC1
+#include "bc1_core.cuh"
+#endif
+
 extern "C" {
+#ifdef HB_BC1
+// in: nblocks x 64 floats RGBA 0..1; out: nblocks x 8 bytes
+void hb_bc1_blocks(const float *in, uint64_t nblocks, float alpha_threshold, int steps, uint8_t *out) {
+	for (uint64_t b = 0; b < nblocks; b++) {
+		uint32_t w[2];
+		b200ic::bc1::encode_block(in + b * 64, alpha_threshold, steps, w);
+		memcpy(out + b * 8, w, 8);
+	}
+}
+#endif
 #ifdef HB_BC7AMD
 static uint32_t *hb_sp_table() {
 	static std::vector<uint32_t> sp;
