@@ -7,11 +7,17 @@
 //   quantise phase : one (partition, subset) of the current mode per lane (16..192 independent optQuantAnD problems)
 //   selection      : rank of every partition's error computed in parallel (stable: ties keep partition order),
 //                    the 8 lowest are shaken
-//   shake phase    : one (attempt, subset) per lane -- ep_shaker_d + ep_shaker_2_d chains are independent
-//   dual-index     : one (rotation, index-selection, vector|scalar) per lane
+//   shake phase    : "tasks" = (attempt, subset) or, for the dual-index modes, (rotation, selection, vector|scalar).
+//                    ep_shaker_d (82 % of the reference's time) is cut into work items (task, (q,p) re-indexing,
+//                    z-slice of the endpoint cube); the items of all tasks are laid out sorted by subset size and
+//                    dealt to the lanes round-robin, so that the lanes of one round run the same trip counts.
+//                    Every item is evaluated with the exact INT32 form of bc7amd_int.cuh; the per-task winner is
+//                    the minimum (error, scan position) key = the reference's first strict minimum.
+//                    ep_shaker_2_d chains run one task per lane.
 //   winners        : first strict minimum in the reference's scan order, by one lane, then broadcast
-// Arithmetic is FP64 like the reference (B200 keeps a full-rate FP64 pipe), which makes the blocks bit-identical
-// to the reference's wherever its qsort tie order does not matter.
+// Arithmetic: FP64 where the reference is FP64 and the operands are not integers (quantiser, endpoint fit), exact
+// INT32 elsewhere; the blocks are bit-identical to the reference's wherever its qsort tie order does not matter.
+// Float sources take the generic FP64 shakers (template parameter U8 = false).
 #include "common.cuh"
 #include "kernels.h"
 #include "bc7amd_block.cuh"
@@ -23,8 +29,9 @@ namespace {
 using namespace amd7;
 
 constexpr int kWarps = 4;
+constexpr int kMaxTasks = 24;   // single-index: 8 attempts x 3 subsets; dual-index: 8 combos x 2
+constexpr int kItemBatch = 160; // work items evaluated between two per-task reductions
 
-__device__ uint32_t *g_sp_table = nullptr;
 uint32_t *g_sp_table_host[16] = {};
 
 struct ShakeOut {
@@ -33,13 +40,31 @@ struct ShakeOut {
 	uint32_t ep[2]; // 4 x 8-bit endpoint codes each
 };
 
+// One ep_shaker_d problem (u8 path)
+struct CubeTask {
+	uint32_t d[16];     // packed texels
+	uint64_t idx_q;     // quantiser indices
+	uint64_t cur;       // collapsed indices of the running pass
+	uint64_t best_idx;  // index_io of the reference
+	uint64_t pass_key;  // best (err << 16 | qp << 8 | lattice << 6 | gray) of the running pass
+	uint64_t pass_idx;
+	real err_o;
+	real mean[4];
+	uint16_t item_base, item_count;
+	uint8_t n, clog, bits, type, Mi, done, all_same, pad;
+};
+
 struct WarpScratch {
 	float in[64];
 	BlockInput B;
 	real serr[64][3];
 	real perr[64];
 	int top[8];
-	ShakeOut so[24];
+	ShakeOut so[kMaxTasks];
+	CubeTask task[kMaxTasks];
+	uint64_t item_key[kItemBatch];
+	uint64_t item_idx[kItemBatch];
+	uint8_t order[kMaxTasks];
 	uint64_t blk[2];
 	real blk_err;
 };
@@ -57,13 +82,142 @@ __device__ __forceinline__ uint64_t pack_idx(const int *idx, int n) {
 	for (int i = 0; i < n; i++) v |= (uint64_t) (idx[i] & 15) << (4 * i);
 	return v;
 }
+__device__ __forceinline__ void unpack_idx(uint64_t v, int *idx, int n) {
+	for (int i = 0; i < n; i++) idx[i] = (int) ((v >> (4 * i)) & 15u);
+}
 __device__ __forceinline__ uint32_t pack_ep(const int e[4]) {
 	return (uint32_t) (e[0] & 255) | ((uint32_t) (e[1] & 255) << 8) | ((uint32_t) (e[2] & 255) << 16) | ((uint32_t) (e[3] & 255) << 24);
 }
 
+// Start (or restart) a pass of ep_shaker_d for one task: collapse the indices, handle the single-index case.
+__device__ __forceinline__ void cube_begin_pass(const Tables &T, CubeTask &t, uint64_t from) {
+	int index[kMaxEntries];
+	unpack_idx(from, index, t.n);
+	const int Mi = collapse_indices(index, t.n);
+	if (Mi == 0) {
+		U8Subset S;
+		for (int i = 0; i < t.n; i++) S.d[i] = t.d[i];
+		S.n = t.n;
+		S.all_same = t.all_same != 0;
+		for (int j = 0; j < 4; j++) S.mean[j] = t.mean[j];
+		const int bits[3] = {t.bits, t.bits, t.bits};
+		int e0[2][4];
+		const real e = shake_single_index_u8(T, S, t.clog, bits, t.type, 3, index, e0);
+		if (e < t.err_o) {
+			t.err_o = e;
+			t.best_idx = pack_idx(index, t.n);
+		}
+		t.done = 1;
+		t.item_count = 0;
+		return;
+	}
+	t.cur = pack_idx(index, t.n);
+	t.Mi = (uint8_t) Mi;
+	t.pass_key = ~0ull;
+	t.pass_idx = 0;
+}
+
+// ep_shaker_d for all tasks of the warp (u8 path). On return task[i].err_o / best_idx hold its result.
+__device__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit, unsigned lane) {
+	if ((int) lane < ntasks) {
+		CubeTask &t = ws.task[lane];
+		t.err_o = A7_HUGE;
+		t.best_idx = t.idx_q;
+		t.done = 0;
+		cube_begin_pass(T, t, t.idx_q);
+	}
+	__syncwarp();
+	for (int pass = 0; pass < 2; pass++) {
+		// ---- lay the items out: tasks sorted by (clog, n) descending so that the lanes of a round agree on trip counts
+		int count = 0, sortkey = -1;
+		if ((int) lane < ntasks && !ws.task[lane].done) {
+			const CubeTask &t = ws.task[lane];
+			count = qp_count(t.Mi, (1 << t.clog) - 1) * zsplit;
+			sortkey = t.clog * 32 + t.n;
+		}
+		int rank = 0;
+		for (int o = 0; o < ntasks; o++) {
+			const int ok = __shfl_sync(FULL, sortkey, o);
+			rank += (ok > sortkey || (ok == sortkey && o < (int) lane)) ? 1 : 0;
+		}
+		if ((int) lane < ntasks) ws.order[rank] = (uint8_t) lane;
+		__syncwarp();
+		const int owner = (int) lane < ntasks ? ws.order[lane] : 0;
+		int mine = __shfl_sync(FULL, count, owner);
+		if ((int) lane >= ntasks) mine = 0;
+		int incl = mine;
+		for (int dlt = 1; dlt < 32; dlt <<= 1) {
+			const int v = __shfl_up_sync(FULL, incl, dlt);
+			if ((int) lane >= dlt) incl += v;
+		}
+		const int total = __shfl_sync(FULL, incl, 31);
+		if ((int) lane < ntasks) {
+			ws.task[owner].item_base = (uint16_t) (incl - mine);
+			ws.task[owner].item_count = (uint16_t) mine;
+		}
+		__syncwarp();
+		if (total == 0) break;
+		for (int b0 = 0; b0 < total; b0 += kItemBatch) {
+			const int b1 = min(total, b0 + kItemBatch);
+			for (int it = b0 + (int) lane; it < b1; it += 32) {
+				int ti = 0;
+				for (int r = 0; r < ntasks; r++) {
+					const int cand = ws.order[r];
+					const int base = ws.task[cand].item_base;
+					if (it >= base && it < base + ws.task[cand].item_count) ti = cand;
+				}
+				const CubeTask &t = ws.task[ti];
+				const int local = it - t.item_base;
+				const int qp = local / zsplit, zp = local - qp * zsplit;
+				int q, p;
+				qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
+				const int bits[3] = {t.bits, t.bits, t.bits};
+				const int zn = 4 / zsplit;
+				uint32_t key;
+				uint64_t idx;
+				if (t.clog == 2) cube_item_u8<2>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx);
+				else cube_item_u8<3>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx);
+				ws.item_key[it - b0] = ((uint64_t) (key >> 8) << 16) | ((uint64_t) qp << 8) | (uint64_t) (key & 255u);
+				ws.item_idx[it - b0] = idx;
+			}
+			__syncwarp();
+			if ((int) lane < ntasks && !ws.task[lane].done) {
+				CubeTask &t = ws.task[lane];
+				const int lo = max(b0, (int) t.item_base), hi = min(b1, (int) t.item_base + (int) t.item_count);
+				for (int it = lo; it < hi; it++)
+					if (ws.item_key[it - b0] < t.pass_key) {
+						t.pass_key = ws.item_key[it - b0];
+						t.pass_idx = ws.item_idx[it - b0];
+					}
+			}
+			__syncwarp();
+		}
+		// ---- per task: the reference's change / better logic (:1372-1400)
+		if ((int) lane < ntasks && !ws.task[lane].done) {
+			CubeTask &t = ws.task[lane];
+			const real err_2 = (real) (uint32_t) (t.pass_key >> 16);
+			const int qp = (int) ((t.pass_key >> 8) & 255u);
+			int q0, p0;
+			qp_decode(qp, t.Mi, (1 << t.clog) - 1, q0, p0);
+			int change = 0;
+			for (int k = 0; k < t.n; k++)
+				change = change || ((int) ((t.cur >> (4 * k)) & 15u) * q0 + p0 != (int) ((t.pass_idx >> (4 * k)) & 15u));
+			const int better = err_2 < t.err_o;
+			if (better) {
+				t.best_idx = t.pass_idx;
+				t.err_o = err_2;
+			}
+			if (!(change && better) || pass == 1) t.done = 1;
+			else cube_begin_pass(T, t, t.pass_idx);
+		}
+		__syncwarp();
+	}
+}
+
 template <bool U8>
 __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) {
-	__shared__ WarpScratch scratch[kWarps];
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 	const uint64_t block = (uint64_t) blockIdx.x * kWarps + warp;
 	if (block >= p.n_blocks) return; // whole warp
@@ -117,27 +271,51 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 				if (rank < attempts) ws.top[rank] = part;
 			}
 			__syncwarp();
-			if ((int) lane < attempts * subsets) {
+			const int ntasks = attempts * subsets;
+			const bool cube_u8 = U8 && sp.dim == 3;
+			real sub[kMaxEntries][4];
+			int n = 0, idx[kMaxEntries], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+			U8Subset S;
+			if ((int) lane < ntasks) {
 				const int a = (int) lane / subsets, s = (int) lane - a * subsets;
-				const int part = ws.top[a];
-				real sub[kMaxEntries][4];
-				int n, idx[kMaxEntries], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-				gather_subset(ws.B, subsets, part, s, sp.dim, sub, n);
-				ShakeOut o;
-				o.err = 0; o.idx = 0; o.ep[0] = o.ep[1] = 0;
-				if (n) {
-					quantise_subset(sub, n, sp.clusters, idx, sp.dim);
-					if (U8) {
-						U8Subset S;
-						make_u8_subset(sub, n, sp.dim, S);
-						o.err = shake_subset_u8(T, sp, S, idx, ep);
-					} else {
-						o.err = shake_subset(T, sp, sub, n, idx, ep);
-					}
-					o.idx = pack_idx(idx, n);
-					o.ep[0] = pack_ep(ep[0]);
-					o.ep[1] = pack_ep(ep[1]);
+				gather_subset(ws.B, subsets, ws.top[a], s, sp.dim, sub, n);
+				quantise_subset(sub, n, sp.clusters, idx, sp.dim);
+				if (U8) make_u8_subset(sub, n, sp.dim, S);
+				if (cube_u8) {
+					CubeTask &t = ws.task[lane];
+					for (int i = 0; i < 16; i++) t.d[i] = i < n ? S.d[i] : 0u;
+					t.idx_q = pack_idx(idx, n);
+					for (int j = 0; j < 4; j++) t.mean[j] = S.mean[j];
+					t.n = (uint8_t) n;
+					t.clog = (uint8_t) ilog2(sp.clusters);
+					t.bits = (uint8_t) sp.bits[0];
+					t.type = (uint8_t) sp.parity;
+					t.all_same = S.all_same ? 1 : 0;
 				}
+			}
+			__syncwarp();
+			if (cube_u8) cube_phase(T, ws, ntasks, 1, lane);
+			if ((int) lane < ntasks) {
+				ShakeOut o;
+				if (!U8) {
+					o.err = shake_subset(T, sp, sub, n, idx, ep);
+				} else if (sp.dim != 3) {
+					o.err = shake_subset_u8(T, sp, S, idx, ep);
+				} else {
+					// shake_subset with the cube result already known (:754-805)
+					const CubeTask &t = ws.task[lane];
+					const int clog = t.clog;
+					const real e0 = t.err_o;
+					real e1 = shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], 3);
+					if (e0 < e1) {
+						unpack_idx(t.best_idx, idx, n);
+						e1 = shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], 3);
+					}
+					o.err = e1;
+				}
+				o.idx = pack_idx(idx, n);
+				o.ep[0] = pack_ep(ep[0]);
+				o.ep[1] = pack_ep(ep[1]);
 				ws.so[lane] = o;
 			}
 			__syncwarp();
@@ -169,10 +347,14 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 		} else {
 			const int nrot = 1 << mi.rotation_bits, nsel = 1 << mi.index_mode_bits;
 			const int combos = nrot * nsel;
-			if ((int) lane < combos * 2) {
+			const int ntasks = combos * 2;
+			real blkv[16][4];
+			int idx[16], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+			int ib = 2, cb = 5;
+			U8Subset S;
+			if ((int) lane < ntasks) {
 				const int combo = (int) lane >> 1, which = (int) lane & 1;
 				const int rot = combo / nsel, isel = combo - rot * nsel;
-				real blkv[16][4];
 				for (int i = 0; i < 16; i++) {
 					if (which == 0) {
 						blkv[i][0] = ws.B.px[i][rotation_channel(rot, 1)];
@@ -183,16 +365,29 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 					}
 					blkv[i][3] = 0;
 				}
-				const int ib = which == 0 ? (isel ? mi.index_bits1 : mi.index_bits0) : (isel ? mi.index_bits0 : mi.index_bits1);
-				const int cb = which == 0 ? mi.vector_bits / 3 : mi.scalar_bits;
-				const int bits[4] = {cb, cb, cb, 6 * cb};
-				int idx[16], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+				ib = which == 0 ? (isel ? mi.index_bits1 : mi.index_bits0) : (isel ? mi.index_bits0 : mi.index_bits1);
+				cb = which == 0 ? mi.vector_bits / 3 : mi.scalar_bits;
 				quantise_subset(blkv, 16, 1 << ib, idx, 3);
+				if (U8) {
+					make_u8_subset(blkv, 16, 3, S);
+					CubeTask &t = ws.task[lane];
+					for (int i = 0; i < 16; i++) t.d[i] = S.d[i];
+					t.idx_q = pack_idx(idx, 16);
+					for (int j = 0; j < 4; j++) t.mean[j] = S.mean[j];
+					t.n = 16;
+					t.clog = (uint8_t) ib;
+					t.bits = (uint8_t) cb;
+					t.type = CART;
+					t.all_same = S.all_same ? 1 : 0;
+				}
+			}
+			__syncwarp();
+			if (U8) cube_phase(T, ws, ntasks, ntasks <= 8 ? 4 : 2, lane);
+			if ((int) lane < ntasks) {
+				const int bits[4] = {cb, cb, cb, 6 * cb};
 				ShakeOut o;
 				if (U8) {
-					U8Subset S;
-					make_u8_subset(blkv, 16, 3, S);
-					shake_cube_u8_any(T, S, idx, ib, bits, CART);
+					unpack_idx(ws.task[lane].best_idx, idx, 16);
 					o.err = shake_window_u8_any(T, S, idx, ep, 6, ib, bits[3], 3);
 				} else {
 					shake_cube(T, blkv, 16, idx, (1 << ib) - 1, bits, CART);
@@ -213,17 +408,17 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 					e += ws.so[2 * c + 1].err / 3.;
 					if (e < be) { be = e; bc = c; }
 				}
-				int ep[2][2][4], idx[2][16];
+				int epp[2][2][4], idxp[2][16];
 				for (int w = 0; w < 2; w++) {
 					const ShakeOut &o = ws.so[2 * bc + w];
 					for (int k = 0; k < 4; k++) {
-						ep[w][0][k] = (int) ((o.ep[0] >> (8 * k)) & 255u);
-						ep[w][1][k] = (int) ((o.ep[1] >> (8 * k)) & 255u);
+						epp[w][0][k] = (int) ((o.ep[0] >> (8 * k)) & 255u);
+						epp[w][1][k] = (int) ((o.ep[1] >> (8 * k)) & 255u);
 					}
-					for (int i = 0; i < 16; i++) idx[w][i] = (int) ((o.idx >> (4 * i)) & 15u);
+					for (int i = 0; i < 16; i++) idxp[w][i] = (int) ((o.idx >> (4 * i)) & 15u);
 				}
 				uint64_t blk[2];
-				pack_dual_index(mode, bc % nsel, bc / nsel, ep, idx, blk);
+				pack_dual_index(mode, bc % nsel, bc / nsel, epp, idxp, blk);
 				ws.blk[0] = blk[0];
 				ws.blk[1] = blk[1];
 				ws.blk_err = be;
@@ -259,6 +454,10 @@ cudaError_t init_bc7amd_tables() {
 	if (e != cudaSuccess) return e;
 	e = cudaMemcpy(d, host, kSpEntries * sizeof(uint32_t), cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(bc7amd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(bc7amd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
+	if (e != cudaSuccess) return e;
 	g_sp_table_host[dev] = d;
 	return cudaSuccess;
 }
@@ -276,12 +475,13 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	p.mode_mask = (uint32_t) opts.amd_mode_mask & 0xffu;
 	if (p.n_blocks == 0) return cudaSuccess;
 	const uint64_t grid = (p.n_blocks + kWarps - 1) / kWarps;
+	const size_t smem = kWarps * sizeof(WarpScratch);
 	// 8-bit sources: every component is an exact integer, the exact INT32 shakers apply (bc7amd_int.cuh)
 	const bool u8 = img.format == B200IC_FMT_R8 || img.format == B200IC_FMT_RG8 || img.format == B200IC_FMT_RGB8 ||
 									img.format == B200IC_FMT_RGB8_SRGB || img.format == B200IC_FMT_RGBA8 || img.format == B200IC_FMT_RGBA8_SRGB ||
 									img.format == B200IC_FMT_BLOCKS_RGBA8;
-	if (u8) bc7amd_kernel<true><<<(unsigned) grid, kWarps * 32, 0, stream>>>(p);
-	else bc7amd_kernel<false><<<(unsigned) grid, kWarps * 32, 0, stream>>>(p);
+	if (u8) bc7amd_kernel<true><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
+	else bc7amd_kernel<false><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 

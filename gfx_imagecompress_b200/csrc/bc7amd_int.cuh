@@ -144,7 +144,8 @@ A7_HD int gray_position(int s) { // p1 with gray(p1) == s, 6 bits
 // All lattices of ep_shaker_d for one (q, p): returns min over (lattice, corner) of err << 8 | lattice << 6 | gray position,
 // and that corner's index assignment (4 bits per texel).
 template <int CLOG>
-A7_HD void cube_search_u8(const U8Subset &S, const int *bits, const real epa[2][4], int use_par, int bcc, uint32_t &best_key, uint64_t &best_idx) {
+A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real epa[2][4], int use_par, int bcc, int z0, int z1, uint32_t &best_key,
+													 uint64_t &best_idx) {
 	constexpr int C = 1 << CLOG;
 	// floor of each ideal endpoint on the parity-0 and parity-1 lattice
 	int fl[2][3][2];
@@ -165,7 +166,7 @@ A7_HD void cube_search_u8(const U8Subset &S, const int *bits, const real epa[2][
 				}
 				for (int x = 0; x < 4; x++) ramp_bytes<CLOG>(ep[0][x & 1], ep[1][x >> 1], &tab[k][x]);
 			}
-			for (int z = 0; z < 4; z++)
+			for (int z = z0; z < z1; z++)
 				for (int y = 0; y < 4; y++) {
 					uint32_t pzy[C];
 #pragma unroll
@@ -177,11 +178,11 @@ A7_HD void cube_search_u8(const U8Subset &S, const int *bits, const real epa[2][
 						for (int c = 0; c < C; c++) pal[c] = pzy[c] | byte_of(tab[0][x], c);
 						uint32_t err = 0;
 						uint64_t idx = 0;
-						for (int i = 0; i < S.n; i++) {
-							const uint32_t d = S.d[i];
+						for (int i = 0; i < n; i++) {
+							const uint32_t di = d[i];
 							uint32_t m = 0xffffffffu;
 #pragma unroll
-							for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], d) << 4) | (uint32_t) c);
+							for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], di) << 4) | (uint32_t) c);
 							err += m >> 4;
 							idx |= (uint64_t) (m & 15u) << (4 * i);
 						}
@@ -190,6 +191,36 @@ A7_HD void cube_search_u8(const U8Subset &S, const int *bits, const real epa[2][
 					}
 				}
 		}
+}
+
+// ---- (q, p) re-indexings of a collapsed index set (the double loop of :1144-1146 / :835-836), as an ordered list
+A7_HD int qp_count(int Mi, int Mi_) {
+	int c = 0;
+	for (int q = 1; q * Mi <= Mi_; q++) c += Mi_ - q * Mi + 1;
+	return c;
+}
+A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
+	for (q = 1;; q++) {
+		const int cnt = Mi_ - q * Mi + 1;
+		if (ord < cnt) { p = ord; return; }
+		ord -= cnt;
+	}
+}
+// One work item of ep_shaker_d: texels d[], collapsed indices (4 bits each), one (q, p), z-slices [z0, z1) of every
+// lattice. key = err << 8 | lattice << 6 | gray position (minimum = first strict minimum in the reference's order).
+template <int CLOG>
+A7_HD void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, const int *bits, int type, int z0, int z1, uint32_t &key,
+												uint64_t &idx) {
+	constexpr int Mi_ = (1 << CLOG) - 1;
+	int cidx[kMaxEntries];
+	for (int k = 0; k < n; k++) cidx[k] = (int) ((collapsed >> (4 * k)) & 15u) * q + p;
+	ClusterStats cs;
+	cluster_stats(d, n, cidx, Mi_, 3, cs);
+	real epa[2][4];
+	fit_endpoints_u8(cs, cidx, n, Mi_, 3, epa);
+	key = 0xffffffffu;
+	idx = 0;
+	cube_search_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
 }
 
 // ep_shaker_d on packed 8-bit data (dimension 3). index_io in/out; returns the SSE (exact integer as real).
@@ -226,7 +257,7 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 				fit_endpoints_u8(cs, cidx, n, Mi_, 3, epa);
 				uint32_t key = 0xffffffffu;
 				uint64_t idx_1 = 0;
-				cube_search_u8<CLOG>(S, bits, epa, use_par, bcc, key, idx_1);
+				cube_search_u8<CLOG>(S.d, n, bits, epa, use_par, bcc, 0, 4, key, idx_1);
 				const uint32_t err_1 = key >> 8;
 				if (err_1 < err_2) {
 					err_2 = err_1;
