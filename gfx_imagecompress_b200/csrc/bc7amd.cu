@@ -90,7 +90,7 @@ __device__ __forceinline__ uint32_t pack_ep(const int e[4]) {
 }
 
 // Start (or restart) a pass of ep_shaker_d for one task: collapse the indices, handle the single-index case.
-__device__ __forceinline__ void cube_begin_pass(const Tables &T, CubeTask &t, uint64_t from) {
+__device__ __noinline__ void cube_begin_pass(const Tables &T, CubeTask &t, uint64_t from) {
 	int index[kMaxEntries];
 	unpack_idx(from, index, t.n);
 	const int Mi = collapse_indices(index, t.n);
@@ -118,7 +118,7 @@ __device__ __forceinline__ void cube_begin_pass(const Tables &T, CubeTask &t, ui
 }
 
 // ep_shaker_d for all tasks of the warp (u8 path). On return task[i].err_o / best_idx hold its result.
-__device__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit, unsigned lane) {
+__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit, unsigned lane) {
 	if ((int) lane < ntasks) {
 		CubeTask &t = ws.task[lane];
 		t.err_o = A7_HUGE;

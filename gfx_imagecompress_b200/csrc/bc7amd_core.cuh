@@ -91,23 +91,35 @@ A7_HD size_t sp_slot(int clog, int bits, int value, int o1, int o2, int i) {
 }
 inline void build_single_point_table(uint32_t *sp) { // init_ramps (:293-345)
 	const uint32_t kEmpty = 0xffffffffu;
+#pragma unroll 1
 	for (size_t i = 0; i < kSpEntries; i++) sp[i] = kEmpty;
+#pragma unroll 1
 	for (int clog = 2; clog < 5; clog++)
+#pragma unroll 1
 		for (int bits = 5; bits < 9; bits++) {
+#pragma unroll 1
 			for (int p1 = 0; p1 < (1 << bits); p1++)
+#pragma unroll 1
 				for (int p2 = 0; p2 < (1 << bits); p2++)
+#pragma unroll 1
 					for (int i = 0; i < (1 << clog); i++) {
 						const int v = ramp_int(expand_bits(bits, p1), expand_bits(bits, p2), i, clog);
 						sp[sp_slot(clog, bits, v, p1 & 1, p2 & 1, i)] = (uint32_t) p1 | ((uint32_t) p2 << 8); // last writer wins
 					}
+#pragma unroll 1
 			for (int o1 = 0; o1 < 2; o1++)
+#pragma unroll 1
 				for (int o2 = 0; o2 < 2; o2++)
+#pragma unroll 1
 					for (int i = 0; i < (1 << clog); i++) {
 						bool exact[256];
+#pragma unroll 1
 						for (int v = 0; v < 256; v++) exact[v] = sp[sp_slot(clog, bits, v, o1, o2, i)] != kEmpty;
+#pragma unroll 1
 						for (int v = 0; v < 256; v++) {
 							if (exact[v]) continue;
 							int k = 1;
+#pragma unroll 1
 							for (; k < 256; k++)
 								if ((v - k >= 0 && exact[v - k]) || (v + k < 256 && exact[v + k])) break;
 							uint32_t src = 0;
@@ -122,6 +134,7 @@ inline void build_single_point_table(uint32_t *sp) { // init_ramps (:293-345)
 // ---- small utilities ---------------------------------------------------------------------------------------
 // order[] = permutation sorting key[] ascending (stable)
 A7_HD void sort_order(const real *key, int *order, int n) {
+#pragma unroll 1
 	for (int i = 0; i < n; i++) {
 		const real k = key[i];
 		int j = i;
@@ -132,21 +145,31 @@ A7_HD void sort_order(const real *key, int *order, int n) {
 A7_HD int ilog2(int v) { int c = 0; while (v >>= 1) c++; return c; }
 
 // eigenVector_d (:336-420): dominant eigenvector by repeated squaring, 3 rounds of 8
-A7_HD void dominant_axis(const real cov[4][4], real axis[4], int dim) {
+A7_HDN void dominant_axis(const real cov[4][4], real axis[4], int dim) {
 	real c[2][4][4];
+#pragma unroll 1
 	for (int i = 0; i < dim; i++)
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) c[0][i][j] = cov[i][j];
 	int l = 0;
+#pragma unroll 1
 	for (int round = 0; round < 3; round++) {
 		real md = 0;
+#pragma unroll 1
 		for (int i = 0; i < dim; i++) md = c[l][i][i] > md ? c[l][i][i] : md;
 		if (md <= 0) return;
+#pragma unroll 1
 		for (int i = 0; i < dim; i++)
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) c[l][i][j] /= md;
+#pragma unroll 1
 		for (int m = 0; m < 8; m++) {
+#pragma unroll 1
 			for (int i = 0; i < dim; i++)
+#pragma unroll 1
 				for (int j = 0; j < dim; j++) {
 					real t = 0;
+#pragma unroll 1
 					for (int k = 0; k < dim; k++) t += c[l][i][k] * c[l][k][j];
 					c[1 - l][i][j] = t;
 				}
@@ -155,34 +178,40 @@ A7_HD void dominant_axis(const real cov[4][4], real axis[4], int dim) {
 	}
 	real md = 0;
 	int k = 0;
+#pragma unroll 1
 	for (int i = 0; i < dim; i++) {
 		k = c[l][i][i] > md ? i : k;
 		md = c[l][i][i] > md ? c[l][i][i] : md;
 	}
 	real t = 0;
+#pragma unroll 1
 	for (int i = 0; i < dim; i++) {
 		t += c[l][k][i] * c[l][k][i];
 		axis[i] = c[l][k][i];
 	}
 	t = sqrt(t);
 	if (t <= 0) return;
+#pragma unroll 1
 	for (int i = 0; i < dim; i++) axis[i] /= t;
 }
 
 // quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of n scalars (lattice A_n* decoding)
-A7_HD void lattice_quantise(const real *v_, int k, int n, int *idx) {
+A7_HDN void lattice_quantise(const real *v_, int k, int n, int *idx) {
 	real m = v_[0], M = v_[0];
+#pragma unroll 1
 	for (int i = 1; i < n; i++) {
 		m = m < v_[i] ? m : v_[i];
 		M = M > v_[i] ? M : v_[i];
 	}
 	if (M == m) {
+#pragma unroll 1
 		for (int i = 0; i < n; i++) idx[i] = 0;
 		return;
 	}
 	const real s = (real) (k - 1) / (M - m);
 	real d[kMaxEntries];
 	real dm = 0, r = 0;
+#pragma unroll 1
 	for (int i = 0; i < n; i++) {
 		const real v = v_[i] * s;
 		const real z = floor(v + 0.5 - m * s);
@@ -193,68 +222,87 @@ A7_HD void lattice_quantise(const real *v_, int k, int n, int *idx) {
 	}
 	if ((real) n * r - dm * dm >= (real) (n - 1) / 4 / 2) {
 		dm /= (real) n;
+#pragma unroll 1
 		for (int i = 0; i < n; i++) d[i] -= dm;
 		int ord[kMaxEntries];
 		sort_order(d, ord, n);
 		real mm = 0, l = 0;
 		int j = -1;
+#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			l += d[ord[i]] - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
 			if (l < mm) { mm = l; j = i; }
 		}
 		j = (j + 1) % n;
+#pragma unroll 1
 		for (int i = j; i < n; i++) idx[ord[i]]++;
 	}
 	int mi = idx[0];
+#pragma unroll 1
 	for (int i = 1; i < n; i++) mi = mi < idx[i] ? mi : idx[i];
+#pragma unroll 1
 	for (int i = 0; i < n; i++) idx[i] -= mi;
 }
 
 // optQuantAnD_d (:1874-2045): PCA line + iterative optimal uniform quantiser. Returns the SSE; index[] out.
 A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *index, int dim) {
 	real cen[kMaxEntries][4], mean[4], cov[4][4];
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) {
 		real m = 0;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) m += data[k][j];
 		if (n) m /= (real) n;
 		mean[j] = m;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) cen[k][j] = data[k][j] - m;
 	}
+#pragma unroll 1
 	for (int i = 0; i < dim; i++)
+#pragma unroll 1
 		for (int j = 0; j <= i; j++) {
 			real c = 0;
+#pragma unroll 1
 			for (int k = 0; k < n; k++) c += cen[k][i] * cen[k][j];
 			cov[i][j] = c;
 			cov[j][i] = c;
 		}
 	real t = 0;
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) t += cov[j][j];
 	if (t < (1. / 256.) || n == 0) {
+#pragma unroll 1
 		for (int i = 0; i < n; i++) index[i] = 0;
 		return 0;
 	}
 	real dir[4] = {0, 0, 0, 0}, proj[kMaxEntries];
 	dominant_axis(cov, dir, dim);
+#pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		real p = 0;
+#pragma unroll 1
 		for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
 		proj[k] = p;
 	}
 	int first[kMaxEntries];
 	int try_two = 50;
 	real s;
+#pragma unroll 1
 	for (int it = 0; it < 200; it++) {
 		if (it) {
 			int done;
 			do {
 				real q = 0;
 				s = t = 0;
+#pragma unroll 1
 				for (int k = 0; k < n; k++) {
 					s += index[k];
 					t += index[k] * index[k];
 				}
+#pragma unroll 1
 				for (int j = 0; j < dim; j++) {
 					real d = 0;
+#pragma unroll 1
 					for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
 					dir[j] = d;
 					q += d * d;
@@ -265,9 +313,12 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 				q = sqrt(q);
 				t *= q;
 				if (q != 0)
+#pragma unroll 1
 					for (int j = 0; j < dim; j++) dir[j] /= q;
+#pragma unroll 1
 				for (int k = 0; k < n; k++) {
 					real p = 0;
+#pragma unroll 1
 					for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
 					proj[k] = p;
 				}
@@ -276,19 +327,23 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 				int k = 0;
 				done = 1;
 				int next[kMaxEntries];
+#pragma unroll 1
 				for (int j = 0; j < n; j++) {
 					while (proj[ord[j]] > ((real) k + 0.5 - s) * t && k < clusters - 1) k++;
 					next[ord[j]] = k;
 				}
+#pragma unroll 1
 				for (int j = 0; j < n; j++) {
 					done = done && (next[j] == index[j]);
 					index[j] = next[j];
 				}
 			} while (!done && try_two--);
 			if (it == 1) {
+#pragma unroll 1
 				for (int j = 0; j < n; j++) first[j] = index[j];
 			} else {
 				done = 1;
+#pragma unroll 1
 				for (int j = 0; j < n; j++) done = done && (first[j] == index[j]);
 				if (done) break;
 			}
@@ -296,12 +351,15 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 		lattice_quantise(proj, clusters, n, index);
 	}
 	s = t = 0;
+#pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		s += index[k];
 		t += index[k] * index[k];
 	}
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) {
 		real d = 0;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
 		dir[j] = d;
 	}
@@ -309,7 +367,9 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 	t = t - s * s * (real) n;
 	t = (t == 0 ? 0. : 1 / t);
 	real err = 0;
+#pragma unroll 1
 	for (int i = 0; i < n; i++)
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) {
 			const real o = mean[j] + dir[j] * t * ((real) index[i] - s);
 			err += (data[i][j] - o) * (data[i][j] - o);
@@ -332,18 +392,22 @@ A7_HD int endpoint_floor(real v, int bits, int use_par, int odd) {
 // index_collapse_ (:513-538); returns the new maximum index
 A7_HD int collapse_indices(int *index, int n) {
 	int mi = index[0], Mi = index[0];
+#pragma unroll 1
 	for (int k = 1; k < n; k++) {
 		mi = mi < index[k] ? mi : index[k];
 		Mi = Mi > index[k] ? Mi : index[k];
 	}
 	int D = 1;
+#pragma unroll 1
 	for (int d = 2; d <= Mi - mi; d++) {
 		int k = 0;
+#pragma unroll 1
 		for (; k < n; k++)
 			if ((index[k] - mi) % d != 0) break;
 		if (k >= n) D = d;
 	}
 	int top = 0;
+#pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		index[k] = (index[k] - mi) / D;
 		top = top > index[k] ? top : index[k];
@@ -352,26 +416,31 @@ A7_HD int collapse_indices(int *index, int n) {
 }
 
 // quant_single_point_d (:546-701): best (endpoints, index) reproducing ONE colour `pt`. Returns per-texel error.
-A7_HD real single_point(const Tables &T, const real pt[4], int clog, const int *bits, int type, int dim, int epo[2][4], int &best_index) {
+A7_HDN real single_point(const Tables &T, const real pt[4], int clog, const int *bits, int type, int dim, int epo[2][4], int &best_index) {
 	const int use_par = type != 0;
 	const int npv = 1 << type; // npv_nd for types 0..2
 	real err0 = A7_HUGE, err1 = A7_HUGE;
 	int idx = 0, idx1 = 0;
 	int e0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 	for (int pn = 0; pn < npv; pn++) {
 		// parity of endpoint 0 / 1 for this vector (identical across channels for CART / SAME_PAR / BCC)
 		const int par0 = type == SAME_PAR ? pn : (pn >> 1), par1 = type == SAME_PAR ? pn : (pn & 1);
 		const int a0 = use_par ? par0 : 0, a1 = use_par ? par0 + 1 : 2;
 		const int b0 = use_par ? par1 : 0, b1 = use_par ? par1 + 1 : 2;
+#pragma unroll 1
 		for (int i = 0; i < (1 << clog); i++) {
 			real t = 0;
 			int t1o[4], t2o[4], dr0[4];
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) {
 				real tbest = A7_HUGE;
 				int tf = (int) floor(pt[j]), tc = (int) ceil(pt[j]);
 				tf = tf < 0 ? 0 : tf;
 				tc = tc > 255 ? 255 : tc;
+#pragma unroll 1
 				for (int t1 = a0; t1 < a1; t1++)
+#pragma unroll 1
 					for (int t2 = b0; t2 < b1; t2++) {
 						const uint32_t ef = T.sp[sp_slot(clog, bits[j], tf, t1, t2, i)] >> 16, ec = T.sp[sp_slot(clog, bits[j], tc, t1, t2, i)] >> 16;
 						int dr;
@@ -386,6 +455,7 @@ A7_HD real single_point(const Tables &T, const real pt[4], int clog, const int *
 			}
 			if (t < err0) {
 				idx = i;
+#pragma unroll 1
 				for (int j = 0; j < dim; j++) {
 					const uint32_t e = T.sp[sp_slot(clog, bits[j], dr0[j], t1o[j], t2o[j], i)];
 					e0[0][j] = (int) (e & 255u);
@@ -397,6 +467,7 @@ A7_HD real single_point(const Tables &T, const real pt[4], int clog, const int *
 		}
 		if (err0 < err1) {
 			idx1 = idx;
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) { epo[0][j] = e0[0][j]; epo[1][j] = e0[1][j]; }
 			err1 = err0;
 		}
@@ -407,7 +478,7 @@ A7_HD real single_point(const Tables &T, const real pt[4], int clog, const int *
 }
 
 // Handles the "every texel takes the same index" case shared by both shakers (:789-826, :1114-1140)
-A7_HD real shake_single_index(const Tables &T, const real data[][4], int n, bool all_same, const real mean[4], int clog, const int *bits,
+A7_HDN real shake_single_index(const Tables &T, const real data[][4], int n, bool all_same, const real mean[4], int clog, const int *bits,
 															int type, int dim, int *index, int epo[2][4]) {
 	int bi;
 	real t;
@@ -416,38 +487,49 @@ A7_HD real shake_single_index(const Tables &T, const real data[][4], int n, bool
 	} else {
 		single_point(T, mean, clog, bits, type, dim, epo, bi);
 		t = 0;
+#pragma unroll 1
 		for (int i = 0; i < n; i++)
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) {
 				const real o = (real) ramp_int(expand_bits(bits[j], epo[0][j]), expand_bits(bits[j], epo[1][j]), bi, clog);
 				t += (data[i][j] - o) * (data[i][j] - o);
 			}
 	}
+#pragma unroll 1
 	for (int i = 0; i < n; i++) index[i] = bi;
 	return t;
 }
 
 // Least-squares endpoints for index assignment cidx[] against rounded cluster means (:858-916 == :1160-1219)
-A7_HD void fit_endpoints(const real data[][4], int n, const int *cidx, int Mi_, int dim, real epa[2][4]) {
+A7_HDN void fit_endpoints(const real data[][4], int n, const int *cidx, int Mi_, int dim, real epa[2][4]) {
 	real cc[16][4];
 	int cnt[16];
+#pragma unroll 1
 	for (int c = 0; c <= Mi_; c++) {
 		cnt[c] = 0;
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) cc[c][j] = 0;
 	}
+#pragma unroll 1
 	for (int i = 0; i < n; i++) {
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) cc[cidx[i]][j] += data[i][j];
 		cnt[cidx[i]]++;
 	}
 	// mean + round of every populated cluster (clusters are independent, so the visit order is irrelevant)
+#pragma unroll 1
 	for (int c = 0; c <= Mi_; c++)
 		if (cnt[c])
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) cc[c][j] = floor(cc[c][j] / (real) cnt[c] + 0.5);
 	real im00 = 0, im01 = 0, im11 = 0, rp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		const int a = Mi_ - cidx[k], b = cidx[k];
 		im00 += a * a;
 		im01 += b * a;
 		im11 += b * b;
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) {
 			rp[0][j] += (real) a * cc[b][j];
 			rp[1][j] += (real) b * cc[b][j];
@@ -455,6 +537,7 @@ A7_HD void fit_endpoints(const real data[][4], int n, const int *cidx, int Mi_, 
 	}
 	const real dd = im00 * im11 - im01 * im01;
 	const real i00 = im11 / dd, i11 = im00 / dd, i01 = -im01 / dd;
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) {
 		epa[0][j] = (i00 * rp[0][j] + i01 * rp[1][j]) * (real) Mi_;
 		epa[1][j] = (i01 * rp[0][j] + i11 * rp[1][j]) * (real) Mi_;
@@ -472,13 +555,18 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 	const int clog = ilog2(Mi_ + 1);
 	const int C = 1 << clog;
 	int index[kMaxEntries];
+#pragma unroll 1
 	for (int k = 0; k < n; k++) index[k] = index_io[k];
 	bool alls = true;
+#pragma unroll 1
 	for (int i = 1; i < n; i++)
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) alls = alls && (data[0][j] == data[i][j]);
 	real mean[4] = {0, 0, 0, 0};
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) {
 		real m = 0;
+#pragma unroll 1
 		for (int i = 0; i < n; i++) m += data[i][j];
 		mean[j] = m / (real) n;
 	}
@@ -491,7 +579,9 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 			int e0[2][4];
 			const real t = shake_single_index(T, data, n, alls, mean, clog, max_bits, type, dim, index, e0);
 			if (t < err_o) {
+#pragma unroll 1
 				for (int k = 0; k < n; k++) index_io[k] = index[k];
+#pragma unroll 1
 				for (int j = 0; j < dim; j++) { epo_code[0][j] = e0[0][j]; epo_code[1][j] = e0[1][j]; }
 				err_o = t;
 			}
@@ -500,19 +590,26 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 		int p0 = -1, q0 = -1;
 		real err_0 = A7_HUGE;
 		int epo_0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 		for (int q = 1; q * Mi <= Mi_; q++)
+#pragma unroll 1
 			for (int p = 0; p <= Mi_ - q * Mi; p++) {
 				int cidx[kMaxEntries];
+#pragma unroll 1
 				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
 				real epa[2][4];
 				fit_endpoints(data, n, cidx, Mi_, dim, epa);
 				real ed[2][2][4];
 				int ep2[2][2][2][4];
 				const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
+#pragma unroll 1
 				for (int j = 0; j < dim; j++)
+#pragma unroll 1
 					for (int pp0 = 0; pp0 < rr; pp0++)
+#pragma unroll 1
 						for (int pp1 = 0; pp1 < rr; pp1++) {
 							int lo[2], hi[2];
+#pragma unroll 1
 							for (int i = 0; i < 2; i++) {
 								const int f = endpoint_floor(epa[i][j], mb, use_par, i ? pp1 : pp0);
 								lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
@@ -520,11 +617,14 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 							}
 							real best = A7_HUGE;
 							int b1 = 0, b2 = 0;
+#pragma unroll 1
 							for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
 								const int e1 = expand_bits(mb, p1);
+#pragma unroll 1
 								for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
 									const int e2 = expand_bits(mb, p2);
 									real t = 0;
+#pragma unroll 1
 									for (int m = n - 1; m >= 0; m--) {
 										const real d = (real) ramp_int(e1, e2, cidx[m], clog) - data[m][j];
 										t += d * d;
@@ -538,12 +638,15 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 						}
 				real err_1 = A7_HUGE;
 				int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 				for (int pn = 0; pn < (1 << type); pn++) {
 					const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
 					real e2 = 0;
+#pragma unroll 1
 					for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
 					if (e2 < err_1) {
 						err_1 = e2;
+#pragma unroll 1
 						for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
 					}
 				}
@@ -551,19 +654,24 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 					err_0 = err_1;
 					p0 = p;
 					q0 = q;
+#pragma unroll 1
 					for (int j = 0; j < dim; j++) { epo_0[0][j] = epo_1[0][j]; epo_0[1][j] = epo_1[1][j]; }
 				}
 			}
 		// re-cluster against the chosen endpoints
 		int e1[4], e2[4];
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) { e1[j] = expand_bits(mb, epo_0[0][j]); e2[j] = expand_bits(mb, epo_0[1][j]); }
 		int idg[kMaxEntries];
 		real err_r = 0;
+#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			real cmin = A7_HUGE;
 			int ci = 0;
+#pragma unroll 1
 			for (int c = 0; c < C; c++) {
 				real t = 0;
+#pragma unroll 1
 				for (int k = 0; k < dim; k++) {
 					const real d = (real) ramp_int(e1[k], e2[k], c, clog) - data[i][k];
 					t += d * d;
@@ -574,10 +682,13 @@ A7_HDN real shake_window(const Tables &T, const real data[][4], int n, int *inde
 			err_r += cmin;
 		}
 		int change = 0;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != idg[k]);
 		const int better = err_r < err_o;
 		if (better) {
+#pragma unroll 1
 			for (int k = 0; k < n; k++) index_io[k] = index[k] = idg[k];
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) { epo_code[0][j] = epo_0[0][j]; epo_code[1][j] = epo_0[1][j]; }
 			err_o = err_r;
 		}
@@ -593,7 +704,9 @@ A7_HD void shake_cube_lattice(const real data[][4], int n, int clog, const int *
 															real &err_1, int *idx_1) {
 	const int C = 1 << clog;
 	int epi[2][3][2];
+#pragma unroll 1
 	for (int j = 0; j < 3; j++)
+#pragma unroll 1
 		for (int i = 0; i < 2; i++) {
 			const int f = endpoint_floor(epa[i][j], bits[j], use_par, (odd ^ (flip & i)) & 1);
 			const int top = (1 << bits[j]) - 1;
@@ -601,14 +714,18 @@ A7_HD void shake_cube_lattice(const real data[][4], int n, int clog, const int *
 			epi[i][j][1] = f + ((top - f < (1 << use_par) ? top - f : (1 << use_par)) & ~use_par);
 		}
 	real r[3][16];
+#pragma unroll 1
 	for (int j = 0; j < 3; j++) {
 		const int e1 = expand_bits(bits[j], epi[0][j][0]), e2 = expand_bits(bits[j], epi[1][j][0]);
+#pragma unroll 1
 		for (int c = 0; c < C; c++) r[j][c] = (real) ramp_int(e1, e2, c, clog);
 	}
 	int s = 0;
+#pragma unroll 1
 	for (int p1 = 0; p1 < 64; p1++) {
 		const int g = p1 & (-p1);
 		int j0 = 0, ei0 = 0, ei1 = 0;
+#pragma unroll 1
 		for (int j = 0; j < 3; j++)
 			if (((g >> (2 * j)) & 3) != 0) {
 				j0 = j;
@@ -618,15 +735,19 @@ A7_HD void shake_cube_lattice(const real data[][4], int n, int clog, const int *
 		s ^= g;
 		{
 			const int e1 = expand_bits(bits[j0], epi[0][j0][ei0]), e2 = expand_bits(bits[j0], epi[1][j0][ei1]);
+#pragma unroll 1
 			for (int c = 0; c < C; c++) r[j0][c] = (real) ramp_int(e1, e2, c, clog);
 		}
 		real err_0 = 0;
 		int idx_0[kMaxEntries];
+#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			real cmin = A7_HUGE;
 			int ci = 0;
+#pragma unroll 1
 			for (int c = 0; c < C; c++) {
 				real t = 0;
+#pragma unroll 1
 				for (int k = 0; k < 3; k++) t += (r[k][c] - data[i][k]) * (r[k][c] - data[i][k]);
 				if (t < cmin) { cmin = t; ci = c; }
 			}
@@ -634,6 +755,7 @@ A7_HD void shake_cube_lattice(const real data[][4], int n, int clog, const int *
 			err_0 += cmin;
 		}
 		if (err_0 < err_1) {
+#pragma unroll 1
 			for (int i = 0; i < n; i++) idx_1[i] = idx_0[i];
 			err_1 = err_0;
 		}
@@ -646,13 +768,18 @@ A7_HDN real shake_cube(const Tables &T, const real data[][4], int n, int *index_
 	const int use_par = (type == BCC || type == SAME_PAR), bcc = (type == BCC);
 	const int clog = ilog2(Mi_ + 1);
 	int index[kMaxEntries];
+#pragma unroll 1
 	for (int k = 0; k < n; k++) index[k] = index_io[k];
 	bool alls = true;
+#pragma unroll 1
 	for (int i = 1; i < n; i++)
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) alls = alls && (data[0][j] == data[i][j]);
 	real mean[4] = {0, 0, 0, 0};
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) {
 		real m = 0;
+#pragma unroll 1
 		for (int i = 0; i < n; i++) m += data[i][j];
 		mean[j] = m / (real) n;
 	}
@@ -664,6 +791,7 @@ A7_HDN real shake_cube(const Tables &T, const real data[][4], int n, int *index_
 			int e0[2][4];
 			const real t = shake_single_index(T, data, n, alls, mean, clog, bits, type, dim, index, e0);
 			if (t < err_o) {
+#pragma unroll 1
 				for (int k = 0; k < n; k++) index_io[k] = index[k];
 				err_o = t;
 			}
@@ -672,19 +800,27 @@ A7_HDN real shake_cube(const Tables &T, const real data[][4], int n, int *index_
 		int p0 = -1, q0 = -1;
 		real err_2 = A7_HUGE;
 		int idx_2[kMaxEntries];
+#pragma unroll 1
 		for (int k = 0; k < n; k++) idx_2[k] = 0;
+#pragma unroll 1
 		for (int q = 1; q * Mi <= Mi_; q++)
+#pragma unroll 1
 			for (int p = 0; p <= Mi_ - q * Mi; p++) {
 				int cidx[kMaxEntries];
+#pragma unroll 1
 				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
 				real epa[2][4];
 				fit_endpoints(data, n, cidx, Mi_, dim, epa);
 				real err_1 = A7_HUGE;
 				int idx_1[kMaxEntries];
+#pragma unroll 1
 				for (int k = 0; k < n; k++) idx_1[k] = 0;
+#pragma unroll 1
 				for (int odd = 0; odd <= use_par; odd++)
+#pragma unroll 1
 					for (int flip = 0; flip <= bcc; flip++) shake_cube_lattice(data, n, clog, bits, epa, use_par, odd, flip, err_1, idx_1);
 				if (err_1 < err_2) {
+#pragma unroll 1
 					for (int i = 0; i < n; i++) idx_2[i] = idx_1[i];
 					err_2 = err_1;
 					p0 = p;
@@ -692,9 +828,11 @@ A7_HDN real shake_cube(const Tables &T, const real data[][4], int n, int *index_
 				}
 			}
 		int change = 0;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != idx_2[k]);
 		const int better = err_2 < err_o;
 		if (better) {
+#pragma unroll 1
 			for (int k = 0; k < n; k++) index_io[k] = index[k] = idx_2[k];
 			err_o = err_2;
 		}
@@ -738,7 +876,7 @@ struct SingleIndexResult {
 // EncodeSingleIndexBlock (:333-538) + the endpoint packing of :846-881.
 // Reference quirk kept: for ONE_PBIT (mode 1) BOTH p-bits are taken from endpoint 1 of the subset (:443-448), after
 // the anchor flip; the p-bit that endpoint 0 was searched with is dropped.
-A7_HD void pack_single_index(int mode, const SingleIndexResult &r, uint64_t out[2]) {
+A7_HDN void pack_single_index(int mode, const SingleIndexResult &r, uint64_t out[2]) {
 	const ModeInfo mi = mode_info(mode);
 	const int dim = mi.alpha == 0 ? 3 : 4;
 	const int cbits = mi.alpha == 0 ? mi.vector_bits / 3 : mi.vector_bits / 4;
@@ -748,35 +886,47 @@ A7_HD void pack_single_index(int mode, const SingleIndexResult &r, uint64_t out[
 	if (mi.subsets == 3) { fix[1] = kBc7Anchor3a[r.partition]; fix[2] = kBc7Anchor3b[r.partition]; }
 	else if (mi.subsets == 2) fix[1] = kBc7Anchor2[r.partition];
 	bool flip[3] = {false, false, false};
+#pragma unroll 1
 	for (int i = 0; i < 16; i++) {
 		const int p = subset_of(mi.subsets, r.partition, i);
 		blk[i] = r.idx[p][cnt[p]++];
+#pragma unroll 1
 		for (int j = 0; j < mi.subsets; j++)
 			if (i == fix[j] && (blk[i] & (1 << (ib - 1)))) flip[j] = true;
 	}
+#pragma unroll 1
 	for (int i = 0; i < 16; i++)
 		if (flip[subset_of(mi.subsets, r.partition, i)]) blk[i] = ((1 << ib) - 1) - blk[i];
 	Bits128 b = {{0, 0}, 0};
 	put_bits(b, 1u << mode, mode + 1);
 	put_bits(b, (uint32_t) r.partition, mi.partition_bits);
 	int col[3][2][4], par[3][2];
+#pragma unroll 1
 	for (int s = 0; s < mi.subsets; s++) {
 		const int a = flip[s] ? 1 : 0;
+#pragma unroll 1
 		for (int e = 0; e < 2; e++) {
 			const int *src = r.ep[s][e ^ a];
 			par[s][e] = 0;
+#pragma unroll 1
 			for (int k = 0; k < 4; k++) col[s][e][k] = (mi.parity != CART) ? (src[k] >> 1) : src[k];
 			if (mi.parity != CART) par[s][e] = src[0] & 1;
 		}
 		if (mi.parity == SAME_PAR) par[s][0] = par[s][1]; // ONE_PBIT quirk
 	}
+#pragma unroll 1
 	for (int k = 0; k < dim; k++)
+#pragma unroll 1
 		for (int s = 0; s < mi.subsets; s++)
+#pragma unroll 1
 			for (int e = 0; e < 2; e++) put_bits(b, (uint32_t) col[s][e][k], cbits);
 	if (mi.parity == SAME_PAR)
+#pragma unroll 1
 		for (int s = 0; s < mi.subsets; s++) put_bits(b, (uint32_t) par[s][0], 1);
 	else if (mi.parity == BCC)
+#pragma unroll 1
 		for (int s = 0; s < mi.subsets; s++) { put_bits(b, (uint32_t) par[s][0], 1); put_bits(b, (uint32_t) par[s][1], 1); }
+#pragma unroll 1
 	for (int i = 0; i < 16; i++) {
 		const int p = subset_of(mi.subsets, r.partition, i);
 		put_bits(b, (uint32_t) blk[i], (i == fix[p]) ? ib - 1 : ib);
@@ -786,7 +936,7 @@ A7_HD void pack_single_index(int mode, const SingleIndexResult &r, uint64_t out[
 }
 
 // EncodeDualIndexBlock (:902-1056)
-A7_HD void pack_dual_index(int mode, int index_selection, int rotation, int ep[2][2][4], int idx[2][16], uint64_t out[2]) {
+A7_HDN void pack_dual_index(int mode, int index_selection, int rotation, int ep[2][2][4], int idx[2][16], uint64_t out[2]) {
 	const ModeInfo mi = mode_info(mode);
 	Bits128 b = {{0, 0}, 0};
 	put_bits(b, 1u << mode, mode + 1);
@@ -795,19 +945,26 @@ A7_HD void pack_dual_index(int mode, int index_selection, int rotation, int ep[2
 	int ibits[2];
 	ibits[0] = index_selection ? mi.index_bits1 : mi.index_bits0;
 	ibits[1] = index_selection ? mi.index_bits0 : mi.index_bits1;
+#pragma unroll 1
 	for (int i = 0; i < 2; i++)
 		if (idx[i][0] & (1 << (ibits[i] - 1))) {
+#pragma unroll 1
 			for (int j = 0; j < 16; j++) idx[i][j] = ((1 << ibits[i]) - 1) - idx[i][j];
+#pragma unroll 1
 			for (int k = 0; k < 4; k++) { const int t = ep[i][0][k]; ep[i][0][k] = ep[i][1][k]; ep[i][1][k] = t; }
 		}
 	const int vbits = mi.vector_bits / 3;
+#pragma unroll 1
 	for (int c = 0; c < 4; c++)
+#pragma unroll 1
 		for (int e = 0; e < 2; e++) {
 			if (c != 3) put_bits(b, (uint32_t) ep[0][e][c], vbits);
 			else put_bits(b, (uint32_t) ep[1][e][0], mi.scalar_bits);
 		}
+#pragma unroll 1
 	for (int i = 0; i < 2; i++) {
 		const int sel = index_selection ? (i ^ 1) : i;
+#pragma unroll 1
 		for (int j = 0; j < 16; j++) put_bits(b, (uint32_t) idx[sel][j], j == 0 ? ibits[sel] - 1 : ibits[sel]);
 	}
 	out[0] = b.w[0];
@@ -821,13 +978,15 @@ struct BlockInput {
 };
 
 // CompressBlock's set-up (:1296-1380): scale to 0..255, alpha classification, mode filter
-A7_HD void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInput &B) {
+A7_HDN void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInput &B) {
 	bool needs_alpha = false, zero_one = false;
 	real mn[4] = {A7_HUGE, A7_HUGE, A7_HUGE, A7_HUGE}, mx[4] = {0, 0, 0, 0};
+#pragma unroll 1
 	for (int i = 0; i < 16; i++) {
 		const float a = in[i * 4 + 3];
 		if (a < 1.0) needs_alpha = true;
 		else if (((double) a >= 0.99999) || ((double) a < 0.00001)) zero_one = true;
+#pragma unroll 1
 		for (int j = 0; j < 4; j++) {
 			const real v = (real) (in[i * 4 + j] * 255.0f);
 			B.px[i][j] = v;
@@ -836,9 +995,11 @@ A7_HD void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInpu
 		}
 	}
 	real range = mx[0] - mn[0];
+#pragma unroll 1
 	for (int j = 1; j < 4; j++) range = range > (mx[j] - mn[j]) ? range : (mx[j] - mn[j]);
 	const bool solid = range < 1e-10;
 	uint32_t mask = valid_mode_mask ? valid_mode_mask : 0xCFu;
+#pragma unroll 1
 	for (int m = 0; m < 8; m++) {
 		if (!(mask & (1u << m))) continue;
 		const int at = mode_info(m).alpha;
@@ -851,8 +1012,10 @@ A7_HD void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInpu
 
 A7_HD void gather_subset(const BlockInput &B, int subsets, int partition, int subset, int dim, real out[][4], int &n) {
 	n = 0;
+#pragma unroll 1
 	for (int i = 0; i < 16; i++)
 		if (subset_of(subsets, partition, i) == subset) {
+#pragma unroll 1
 			for (int j = 0; j < 4; j++) out[n][j] = j < dim ? B.px[i][j] : 0;
 			n++;
 		}

@@ -23,6 +23,7 @@ A7_HD uint32_t sq_dist4(uint32_t a, uint32_t b) { // sum over the 4 bytes of (a_
 	return __dp4a(ad, ad, 0u);
 #else
 	uint32_t t = 0;
+#pragma unroll 1
 	for (int k = 0; k < 4; k++) {
 		const int d = (int) ((a >> (8 * k)) & 255u) - (int) ((b >> (8 * k)) & 255u);
 		t += (uint32_t) (d * d);
@@ -54,29 +55,37 @@ struct ClusterStats {
 	int sum[16][4];
 };
 // per-cluster counts and channel sums of packed texels d[] under index assignment cidx[]
-A7_HD void cluster_stats(const uint32_t *d, int n, const int *cidx, int Mi_, int dim, ClusterStats &cs) {
+A7_HDN void cluster_stats(const uint32_t *d, int n, const int *cidx, int Mi_, int dim, ClusterStats &cs) {
+#pragma unroll 1
 	for (int c = 0; c <= Mi_; c++) {
 		cs.cnt[c] = 0;
+#pragma unroll 1
 		for (int j = 0; j < 4; j++) cs.sum[c][j] = 0;
 	}
+#pragma unroll 1
 	for (int i = 0; i < n; i++) {
 		const int c = cidx[i];
 		cs.cnt[c]++;
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) cs.sum[c][j] += (int) ((d[i] >> (8 * j)) & 255u);
 	}
 }
 // fit_endpoints on exact-integer data (same FP64 operations as the reference; sums of integers are exact)
-A7_HD void fit_endpoints_u8(const ClusterStats &cs, const int *cidx, int n, int Mi_, int dim, real epa[2][4]) {
+A7_HDN void fit_endpoints_u8(const ClusterStats &cs, const int *cidx, int n, int Mi_, int dim, real epa[2][4]) {
 	real cc[16][4];
+#pragma unroll 1
 	for (int c = 0; c <= Mi_; c++)
 		if (cs.cnt[c])
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) cc[c][j] = floor((real) cs.sum[c][j] / (real) cs.cnt[c] + 0.5);
 	real im00 = 0, im01 = 0, im11 = 0, rp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		const int a = Mi_ - cidx[k], b = cidx[k];
 		im00 += a * a;
 		im01 += b * a;
 		im11 += b * b;
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) {
 			rp[0][j] += (real) a * cc[b][j];
 			rp[1][j] += (real) b * cc[b][j];
@@ -84,6 +93,7 @@ A7_HD void fit_endpoints_u8(const ClusterStats &cs, const int *cidx, int n, int 
 	}
 	const real dd = im00 * im11 - im01 * im01;
 	const real i00 = im11 / dd, i11 = im00 / dd, i01 = -im01 / dd;
+#pragma unroll 1
 	for (int j = 0; j < dim; j++) {
 		epa[0][j] = (i00 * rp[0][j] + i01 * rp[1][j]) * (real) Mi_;
 		epa[1][j] = (i01 * rp[0][j] + i11 * rp[1][j]) * (real) Mi_;
@@ -100,8 +110,10 @@ A7_HD void make_u8_subset(const real data[][4], int n, int dim, U8Subset &S) {
 	S.n = n;
 	int sum[4] = {0, 0, 0, 0};
 	bool same = true;
+#pragma unroll 1
 	for (int i = 0; i < n; i++) {
 		uint32_t v = 0;
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) {
 			const int b = (int) data[i][j];
 			v |= (uint32_t) b << (8 * j);
@@ -111,25 +123,30 @@ A7_HD void make_u8_subset(const real data[][4], int n, int dim, U8Subset &S) {
 		same = same && (v == S.d[0]);
 	}
 	S.all_same = same;
+#pragma unroll 1
 	for (int j = 0; j < 4; j++) S.mean[j] = j < dim ? (real) sum[j] / (real) n : 0;
 }
 
 // the Mi == 0 path of both shakers on packed data (see shake_single_index)
-A7_HD real shake_single_index_u8(const Tables &T, const U8Subset &S, int clog, const int *bits, int type, int dim, int *index, int epo[2][4]) {
+A7_HDN real shake_single_index_u8(const Tables &T, const U8Subset &S, int clog, const int *bits, int type, int dim, int *index, int epo[2][4]) {
 	int bi;
 	real t;
 	if (S.all_same) {
 		real pt[4];
+#pragma unroll 1
 		for (int j = 0; j < 4; j++) pt[j] = (real) ((S.d[0] >> (8 * j)) & 255u);
 		t = single_point(T, pt, clog, bits, type, dim, epo, bi) * (real) S.n;
 	} else {
 		single_point(T, S.mean, clog, bits, type, dim, epo, bi);
 		uint32_t o = 0;
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) o |= (uint32_t) ramp_int(expand_bits(bits[j], epo[0][j]), expand_bits(bits[j], epo[1][j]), bi, clog) << (8 * j);
 		uint32_t e = 0;
+#pragma unroll 1
 		for (int i = 0; i < S.n; i++) e += sq_dist4(S.d[i], o);
 		t = (real) e;
 	}
+#pragma unroll 1
 	for (int i = 0; i < S.n; i++) index[i] = bi;
 	return t;
 }
@@ -149,24 +166,34 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 	constexpr int C = 1 << CLOG;
 	// floor of each ideal endpoint on the parity-0 and parity-1 lattice
 	int fl[2][3][2];
+#pragma unroll 1
 	for (int e = 0; e < 2; e++)
+#pragma unroll 1
 		for (int k = 0; k < 3; k++)
+#pragma unroll 1
 			for (int par = 0; par <= use_par; par++) fl[e][k][par] = endpoint_floor(epa[e][k], bits[k], use_par, par);
 	int lattice = 0;
+#pragma unroll 1
 	for (int odd = 0; odd <= use_par; odd++)
+#pragma unroll 1
 		for (int flip = 0; flip <= bcc; flip++, lattice++) {
 			uint64_t tab[3][4]; // [channel][ei0 + 2*ei1] -> C ramp bytes
+#pragma unroll 1
 			for (int k = 0; k < 3; k++) {
 				int ep[2][2];
+#pragma unroll 1
 				for (int e = 0; e < 2; e++) {
 					const int f = fl[e][k][(odd ^ (flip & e)) & 1];
 					const int top = (1 << bits[k]) - 1;
 					ep[e][0] = expand_bits(bits[k], f);
 					ep[e][1] = expand_bits(bits[k], f + ((top - f < (1 << use_par) ? top - f : (1 << use_par)) & ~use_par));
 				}
+#pragma unroll 1
 				for (int x = 0; x < 4; x++) ramp_bytes<CLOG>(ep[0][x & 1], ep[1][x >> 1], &tab[k][x]);
 			}
+#pragma unroll 1
 			for (int z = z0; z < z1; z++)
+#pragma unroll 1
 				for (int y = 0; y < 4; y++) {
 					uint32_t pzy[C];
 #pragma unroll
@@ -178,6 +205,7 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 						for (int c = 0; c < C; c++) pal[c] = pzy[c] | byte_of(tab[0][x], c);
 						uint32_t err = 0;
 						uint64_t idx = 0;
+#pragma unroll 1
 						for (int i = 0; i < n; i++) {
 							const uint32_t di = d[i];
 							uint32_t m = 0xffffffffu;
@@ -196,10 +224,12 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 // ---- (q, p) re-indexings of a collapsed index set (the double loop of :1144-1146 / :835-836), as an ordered list
 A7_HD int qp_count(int Mi, int Mi_) {
 	int c = 0;
+#pragma unroll 1
 	for (int q = 1; q * Mi <= Mi_; q++) c += Mi_ - q * Mi + 1;
 	return c;
 }
 A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
+#pragma unroll 1
 	for (q = 1;; q++) {
 		const int cnt = Mi_ - q * Mi + 1;
 		if (ord < cnt) { p = ord; return; }
@@ -209,10 +239,11 @@ A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
 // One work item of ep_shaker_d: texels d[], collapsed indices (4 bits each), one (q, p), z-slices [z0, z1) of every
 // lattice. key = err << 8 | lattice << 6 | gray position (minimum = first strict minimum in the reference's order).
 template <int CLOG>
-A7_HD void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, const int *bits, int type, int z0, int z1, uint32_t &key,
+A7_HDN void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, const int *bits, int type, int z0, int z1, uint32_t &key,
 												uint64_t &idx) {
 	constexpr int Mi_ = (1 << CLOG) - 1;
 	int cidx[kMaxEntries];
+#pragma unroll 1
 	for (int k = 0; k < n; k++) cidx[k] = (int) ((collapsed >> (4 * k)) & 15u) * q + p;
 	ClusterStats cs;
 	cluster_stats(d, n, cidx, Mi_, 3, cs);
@@ -230,6 +261,7 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 	const int n = S.n;
 	const int use_par = (type == BCC || type == SAME_PAR), bcc = (type == BCC);
 	int index[kMaxEntries];
+#pragma unroll 1
 	for (int k = 0; k < n; k++) index[k] = index_io[k];
 	real err_o = A7_HUGE;
 	int maxTry = 1, done;
@@ -239,6 +271,7 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 			int e0[2][4];
 			const real t = shake_single_index_u8(T, S, CLOG, bits, type, 3, index, e0);
 			if (t < err_o) {
+#pragma unroll 1
 				for (int k = 0; k < n; k++) index_io[k] = index[k];
 				err_o = t;
 			}
@@ -247,9 +280,12 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 		int p0 = -1, q0 = -1;
 		uint32_t err_2 = 0xffffffffu;
 		uint64_t idx_2 = 0;
+#pragma unroll 1
 		for (int q = 1; q * Mi <= Mi_; q++)
+#pragma unroll 1
 			for (int p = 0; p <= Mi_ - q * Mi; p++) {
 				int cidx[kMaxEntries];
+#pragma unroll 1
 				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
 				ClusterStats cs;
 				cluster_stats(S.d, n, cidx, Mi_, 3, cs);
@@ -267,9 +303,11 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 				}
 			}
 		int change = 0;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != (int) ((idx_2 >> (4 * k)) & 15u));
 		const int better = (real) err_2 < err_o;
 		if (better) {
+#pragma unroll 1
 			for (int k = 0; k < n; k++) index_io[k] = index[k] = (int) ((idx_2 >> (4 * k)) & 15u);
 			err_o = (real) err_2;
 		}
@@ -289,9 +327,12 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
 	const int max_bits[4] = {mb, mb, mb, mb};
 	int index[kMaxEntries];
+#pragma unroll 1
 	for (int k = 0; k < n; k++) index[k] = index_io[k];
 	int sq_total[4] = {0, 0, 0, 0}; // sum of squares of the data per channel
+#pragma unroll 1
 	for (int i = 0; i < n; i++)
+#pragma unroll 1
 		for (int j = 0; j < dim; j++) {
 			const int b = (int) ((S.d[i] >> (8 * j)) & 255u);
 			sq_total[j] += b * b;
@@ -304,7 +345,9 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 			int e0[2][4];
 			const real t = shake_single_index_u8(T, S, CLOG, max_bits, type, dim, index, e0);
 			if (t < err_o) {
+#pragma unroll 1
 				for (int k = 0; k < n; k++) index_io[k] = index[k];
+#pragma unroll 1
 				for (int j = 0; j < dim; j++) { epo_code[0][j] = e0[0][j]; epo_code[1][j] = e0[1][j]; }
 				err_o = t;
 			}
@@ -313,9 +356,12 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 		int p0 = -1, q0 = -1;
 		int64_t err_0 = INT64_MAX;
 		int epo_0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 		for (int q = 1; q * Mi <= Mi_; q++)
+#pragma unroll 1
 			for (int p = 0; p <= Mi_ - q * Mi; p++) {
 				int cidx[kMaxEntries];
+#pragma unroll 1
 				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
 				ClusterStats cs;
 				cluster_stats(S.d, n, cidx, Mi_, dim, cs);
@@ -323,18 +369,24 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 				fit_endpoints_u8(cs, cidx, n, Mi_, dim, epa);
 				int ed[2][2][4], ep2[2][2][2][4];
 				const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
+#pragma unroll 1
 				for (int j = 0; j < dim; j++)
+#pragma unroll 1
 					for (int pp0 = 0; pp0 < rr; pp0++)
+#pragma unroll 1
 						for (int pp1 = 0; pp1 < rr; pp1++) {
 							int lo[2], hi[2];
+#pragma unroll 1
 							for (int i = 0; i < 2; i++) {
 								const int f = endpoint_floor(epa[i][j], mb, use_par, i ? pp1 : pp0);
 								lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
 								hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
 							}
 							int best = INT32_MAX, b1 = 0, b2 = 0;
+#pragma unroll 1
 							for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
 								const int e1 = expand_bits(mb, p1);
+#pragma unroll 1
 								for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
 									uint64_t rv[W];
 									ramp_bytes<CLOG>(e1, expand_bits(mb, p2), rv);
@@ -354,12 +406,15 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 						}
 				int64_t err_1 = INT64_MAX;
 				int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
 				for (int pn = 0; pn < (1 << type); pn++) {
 					const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
 					int64_t e2 = 0;
+#pragma unroll 1
 					for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
 					if (e2 < err_1) {
 						err_1 = e2;
+#pragma unroll 1
 						for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
 					}
 				}
@@ -367,6 +422,7 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 					err_0 = err_1;
 					p0 = p;
 					q0 = q;
+#pragma unroll 1
 					for (int j = 0; j < dim; j++) { epo_0[0][j] = epo_1[0][j]; epo_0[1][j] = epo_1[1][j]; }
 				}
 			}
@@ -374,6 +430,7 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 		uint32_t pal[C];
 		{
 			uint64_t rb[4][W];
+#pragma unroll 1
 			for (int j = 0; j < 4; j++) {
 				rb[j][0] = 0;
 				if (W > 1) rb[j][W - 1] = 0;
@@ -386,6 +443,7 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 		}
 		uint32_t err_r = 0;
 		uint64_t idg = 0;
+#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			uint32_t m = 0xffffffffu;
 #pragma unroll
@@ -394,10 +452,13 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 			idg |= (uint64_t) (m & 15u) << (4 * i);
 		}
 		int change = 0;
+#pragma unroll 1
 		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != (int) ((idg >> (4 * k)) & 15u));
 		const int better = (real) err_r < err_o;
 		if (better) {
+#pragma unroll 1
 			for (int k = 0; k < n; k++) index_io[k] = index[k] = (int) ((idg >> (4 * k)) & 15u);
+#pragma unroll 1
 			for (int j = 0; j < dim; j++) { epo_code[0][j] = epo_0[0][j]; epo_code[1][j] = epo_0[1][j]; }
 			err_o = (real) err_r;
 		}
@@ -421,11 +482,13 @@ A7_HD real shake_subset_u8(const Tables &T, const ShakeParams &sp, const U8Subse
 	const int clog = ilog2(sp.clusters);
 	if (sp.dim != 3) return shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], sp.dim);
 	int tmp[kMaxEntries];
+#pragma unroll 1
 	for (int k = 0; k < S.n; k++) tmp[k] = idx[k];
 	const real e0 = shake_cube_u8_any(T, S, tmp, clog, sp.bits, sp.parity);
 	real e1 = shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], sp.dim);
 	if (e0 < e1) {
 		e1 = shake_window_u8_any(T, S, tmp, ep, sp.shake_size, clog, sp.bits[3], sp.dim);
+#pragma unroll 1
 		for (int k = 0; k < S.n; k++) idx[k] = tmp[k];
 	}
 	return e1;
