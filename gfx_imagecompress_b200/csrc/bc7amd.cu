@@ -34,6 +34,13 @@ constexpr int kItemBatch = 160; // work items evaluated between two per-task red
 
 uint32_t *g_sp_table_host[16] = {};
 
+// Quantise-phase task order: (partition, subset) pairs of each partition table sorted by subset size (descending),
+// so that the 32 lanes of one round run optQuantAnD problems of (nearly) the same size. Pure scheduling data.
+__constant__ uint8_t c_qorder[48 + 192 + 128];
+__device__ __forceinline__ const uint8_t *quantise_order(int subsets, int nparts) {
+	return subsets == 3 ? (nparts == 16 ? c_qorder : c_qorder + 48) : c_qorder + 240;
+}
+
 struct ShakeOut {
 	real err;
 	uint64_t idx; // 4 bits per subset-local entry
@@ -58,6 +65,7 @@ struct WarpScratch {
 	float in[64];
 	BlockInput B;
 	real serr[64][3];
+	uint64_t qidx[64][3]; // quantiser indices of every (partition, subset) of the running mode
 	real perr[64];
 	int top[8];
 	ShakeOut so[kMaxTasks];
@@ -215,7 +223,7 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 }
 
 template <bool U8>
-__global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) {
+__global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -246,12 +254,15 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 		if (mi.alpha != 2) {
 			const ShakeParams sp = single_index_shake_params(mode);
 			const int nparts = 1 << mi.partition_bits, subsets = mi.subsets;
-			for (int t = (int) lane; t < nparts * subsets; t += 32) {
+			const uint8_t *qorder = subsets > 1 ? quantise_order(subsets, nparts) : nullptr;
+			for (int tt = (int) lane; tt < nparts * subsets; tt += 32) {
+				const int t = qorder ? qorder[tt] : tt;
 				const int part = t / subsets, s = t - part * subsets;
 				real sub[kMaxEntries][4];
 				int n, idx[kMaxEntries];
 				gather_subset(ws.B, subsets, part, s, sp.dim, sub, n);
 				ws.serr[part][s] = n ? quantise_subset(sub, n, sp.clusters, idx, sp.dim) : 0;
+				ws.qidx[part][s] = pack_idx(idx, n);
 			}
 			__syncwarp();
 			for (int part = (int) lane; part < nparts; part += 32) {
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(kWarps * 32) bc7amd_kernel(const AmdParams p) 
 			if ((int) lane < ntasks) {
 				const int a = (int) lane / subsets, s = (int) lane - a * subsets;
 				gather_subset(ws.B, subsets, ws.top[a], s, sp.dim, sub, n);
-				quantise_subset(sub, n, sp.clusters, idx, sp.dim);
+				unpack_idx(ws.qidx[ws.top[a]][s], idx, n);
 				if (U8) make_u8_subset(sub, n, sp.dim, S);
 				if (cube_u8) {
 					CubeTask &t = ws.task[lane];
@@ -454,6 +465,22 @@ cudaError_t init_bc7amd_tables() {
 	if (e != cudaSuccess) return e;
 	e = cudaMemcpy(d, host, kSpEntries * sizeof(uint32_t), cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) return e;
+	{
+		uint8_t order[48 + 192 + 128];
+		int pos = 0;
+		for (int table = 0; table < 3; table++) {
+			const int subsets = table < 2 ? 3 : 2, nparts = table == 0 ? 16 : 64;
+			for (int size = 16; size >= 0; size--)
+				for (int t = 0; t < nparts * subsets; t++) {
+					const int part = t / subsets, s = t % subsets;
+					int n = 0;
+					for (int i = 0; i < 16; i++) n += subset_of(subsets, part, i) == s ? 1 : 0;
+					if (n == size) order[pos++] = (uint8_t) t;
+				}
+		}
+		e = cudaMemcpyToSymbol(c_qorder, order, sizeof(order));
+		if (e != cudaSuccess) return e;
+	}
 	e = cudaFuncSetAttribute(bc7amd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(bc7amd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));

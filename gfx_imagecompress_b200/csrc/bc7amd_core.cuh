@@ -132,14 +132,19 @@ inline void build_single_point_table(uint32_t *sp) { // init_ramps (:293-345)
 }
 
 // ---- small utilities ---------------------------------------------------------------------------------------
-// order[] = permutation sorting key[] ascending (stable)
+// order[] = permutation sorting key[] ascending, equal keys in original order (what an insertion sort with the
+// reference's comparator `a - b > 0` produces). Rank counting: fixed trip counts, no data-dependent branches.
 A7_HD void sort_order(const real *key, int *order, int n) {
 #pragma unroll 1
 	for (int i = 0; i < n; i++) {
 		const real k = key[i];
-		int j = i;
-		while (j > 0 && key[order[j - 1]] - k > 0) { order[j] = order[j - 1]; j--; }
-		order[j] = i;
+		int rank = 0;
+#pragma unroll 1
+		for (int j = 0; j < n; j++) {
+			const real kj = key[j];
+			rank += ((k - kj > 0) || (!(kj - k > 0) && j < i)) ? 1 : 0;
+		}
+		order[rank] = i;
 	}
 }
 A7_HD int ilog2(int v) { int c = 0; while (v >>= 1) c++; return c; }
@@ -322,20 +327,21 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 					for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
 					proj[k] = p;
 				}
-				int ord[kMaxEntries];
-				sort_order(proj, ord, n);
-				int k = 0;
+				// The reference sorts the projections and walks the cluster boundaries (k + 0.5 - s) * t with one
+				// running k (:1977-1984). The boundaries are non-decreasing in k (t >= 0), so for sorted input the
+				// running k of an element equals the NUMBER of boundaries it exceeds: no sort, no dependent loop.
+				real bound[15];
+#pragma unroll 1
+				for (int k = 0; k < clusters - 1; k++) bound[k] = ((real) k + 0.5 - s) * t;
 				done = 1;
-				int next[kMaxEntries];
 #pragma unroll 1
 				for (int j = 0; j < n; j++) {
-					while (proj[ord[j]] > ((real) k + 0.5 - s) * t && k < clusters - 1) k++;
-					next[ord[j]] = k;
-				}
+					const real pj = proj[j];
+					int k = 0;
 #pragma unroll 1
-				for (int j = 0; j < n; j++) {
-					done = done && (next[j] == index[j]);
-					index[j] = next[j];
+					for (int b = 0; b < clusters - 1; b++) k += (pj > bound[b]) ? 1 : 0;
+					done = done && (k == index[j]);
+					index[j] = k;
 				}
 			} while (!done && try_two--);
 			if (it == 1) {
