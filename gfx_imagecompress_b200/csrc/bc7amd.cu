@@ -57,8 +57,13 @@ struct CubeTask {
 	uint64_t pass_idx;
 	real err_o;
 	real mean[4];
+	// ep_shaker_2_d state
+	uint64_t w_index;   // running indices (uncollapsed)
+	uint64_t w_best_idx, w_best_ep;
+	real w_err_o;
 	uint16_t item_base, item_count;
-	uint8_t n, clog, bits, type, Mi, done, all_same, pad;
+	uint8_t n, clog, bits, type, Mi, done, all_same, dim;
+	uint8_t w_bits_total, w_size, w_tries, w_active;
 };
 
 struct WarpScratch {
@@ -222,6 +227,153 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 	}
 }
 
+// Lay out the work items of the running pass: tasks sorted by (clog, n) descending so that the lanes of a round agree
+// on trip counts; task[i].item_base / item_count, ws.order. Returns the total number of items.
+__device__ __forceinline__ int layout_items(WarpScratch &ws, int ntasks, int count, int sortkey, unsigned lane) {
+	int rank = 0;
+	for (int o = 0; o < ntasks; o++) {
+		const int ok = __shfl_sync(FULL, sortkey, o);
+		rank += (ok > sortkey || (ok == sortkey && o < (int) lane)) ? 1 : 0;
+	}
+	if ((int) lane < ntasks) ws.order[rank] = (uint8_t) lane;
+	__syncwarp();
+	const int owner = (int) lane < ntasks ? ws.order[lane] : 0;
+	int mine = __shfl_sync(FULL, count, owner);
+	if ((int) lane >= ntasks) mine = 0;
+	int incl = mine;
+	for (int dlt = 1; dlt < 32; dlt <<= 1) {
+		const int v = __shfl_up_sync(FULL, incl, dlt);
+		if ((int) lane >= dlt) incl += v;
+	}
+	const int total = __shfl_sync(FULL, incl, 31);
+	if ((int) lane < ntasks) {
+		ws.task[owner].item_base = (uint16_t) (incl - mine);
+		ws.task[owner].item_count = (uint16_t) mine;
+	}
+	__syncwarp();
+	return total;
+}
+__device__ __forceinline__ int item_owner(const WarpScratch &ws, int ntasks, int it) {
+	int ti = 0;
+	for (int r = 0; r < ntasks; r++) {
+		const int cand = ws.order[r];
+		const int base = ws.task[cand].item_base;
+		if (it >= base && it < base + ws.task[cand].item_count) ti = cand;
+	}
+	return ti;
+}
+
+// Start a round of ep_shaker_2_d for one task (:785-827): collapse, single-index case.
+__device__ __noinline__ void window_begin_round(const Tables &T, CubeTask &t) {
+	int index[kMaxEntries];
+	unpack_idx(t.w_index, index, t.n);
+	const int Mi = collapse_indices(index, t.n);
+	if (Mi == 0) {
+		U8Subset S;
+		for (int i = 0; i < t.n; i++) S.d[i] = t.d[i];
+		S.n = t.n;
+		S.all_same = t.all_same != 0;
+		for (int j = 0; j < 4; j++) S.mean[j] = t.mean[j];
+		const int mb = (t.w_bits_total + 2 * t.dim - 1) / (2 * t.dim);
+		const int bits[4] = {mb, mb, mb, mb};
+		int e0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+		const real e = shake_single_index_u8(T, S, t.clog, bits, t.w_bits_total % (2 * t.dim), t.dim, index, e0);
+		if (e < t.w_err_o) {
+			t.w_err_o = e;
+			t.w_best_idx = pack_idx(index, t.n);
+			t.w_best_ep = pack_ep8(e0);
+		}
+		t.done = 1;
+		t.item_count = 0;
+		return;
+	}
+	t.cur = pack_idx(index, t.n);
+	t.Mi = (uint8_t) Mi;
+	t.pass_key = ~0ull;
+	t.pass_idx = 0;
+}
+
+// ep_shaker_2_d for the tasks with w_active set, starting from task.w_index (u8 path). Results in w_err_o /
+// w_best_idx / w_best_ep.
+__device__ __noinline__ void window_phase(const Tables &T, WarpScratch &ws, int ntasks, unsigned lane) {
+	if ((int) lane < ntasks) {
+		CubeTask &t = ws.task[lane];
+		t.done = t.w_active ? 0 : 1;
+		if (t.w_active) {
+			t.w_err_o = A7_HUGE;
+			t.w_best_idx = t.w_index;
+			t.w_best_ep = 0;
+			t.w_tries = 8;
+			window_begin_round(T, t);
+		}
+	}
+	__syncwarp();
+	for (int round = 0; round < 9; round++) {
+		int count = 0, sortkey = -1;
+		if ((int) lane < ntasks && !ws.task[lane].done) {
+			const CubeTask &t = ws.task[lane];
+			count = qp_count(t.Mi, (1 << t.clog) - 1);
+			sortkey = t.clog * 32 + t.n;
+		}
+		const int total = layout_items(ws, ntasks, count, sortkey, lane);
+		if (total == 0) break;
+		for (int b0 = 0; b0 < total; b0 += kItemBatch) {
+			const int b1 = min(total, b0 + kItemBatch);
+			for (int it = b0 + (int) lane; it < b1; it += 32) {
+				const CubeTask &t = ws.task[item_owner(ws, ntasks, it)];
+				const int qp = it - t.item_base;
+				int q, p;
+				qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
+				uint64_t epo;
+				uint32_t err;
+				if (t.clog == 2) err = window_item_u8<2>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
+				else if (t.clog == 3) err = window_item_u8<3>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
+				else err = window_item_u8<4>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
+				ws.item_key[it - b0] = ((uint64_t) err << 8) | (uint64_t) (255 - qp); // `<=`: the LAST minimum wins
+				ws.item_idx[it - b0] = epo;
+			}
+			__syncwarp();
+			if ((int) lane < ntasks && !ws.task[lane].done) {
+				CubeTask &t = ws.task[lane];
+				const int lo = max(b0, (int) t.item_base), hi = min(b1, (int) t.item_base + (int) t.item_count);
+				for (int it = lo; it < hi; it++)
+					if (ws.item_key[it - b0] < t.pass_key) {
+						t.pass_key = ws.item_key[it - b0];
+						t.pass_idx = ws.item_idx[it - b0];
+					}
+			}
+			__syncwarp();
+		}
+		if ((int) lane < ntasks && !ws.task[lane].done) {
+			CubeTask &t = ws.task[lane];
+			const int qp = 255 - (int) (t.pass_key & 255u);
+			int q0, p0;
+			qp_decode(qp, t.Mi, (1 << t.clog) - 1, q0, p0);
+			const int mb = (t.w_bits_total + 2 * t.dim - 1) / (2 * t.dim);
+			uint64_t idg;
+			uint32_t err_r;
+			if (t.clog == 2) err_r = recluster_u8<2>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
+			else if (t.clog == 3) err_r = recluster_u8<3>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
+			else err_r = recluster_u8<4>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
+			int change = 0;
+			for (int k = 0; k < t.n; k++) change = change || ((int) ((t.cur >> (4 * k)) & 15u) * q0 + p0 != (int) ((idg >> (4 * k)) & 15u));
+			const int better = (real) err_r < t.w_err_o;
+			if (better) {
+				t.w_best_idx = t.w_index = idg;
+				t.w_best_ep = t.pass_idx;
+				t.w_err_o = (real) err_r;
+			}
+			if (!(change && better) || t.w_tries == 0) {
+				t.done = 1;
+			} else {
+				t.w_tries--;
+				window_begin_round(T, t);
+			}
+		}
+		__syncwarp();
+	}
+}
+
 template <bool U8>
 __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,13 +438,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 			const bool cube_u8 = U8 && sp.dim == 3;
 			real sub[kMaxEntries][4];
 			int n = 0, idx[kMaxEntries], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-			U8Subset S;
 			if ((int) lane < ntasks) {
 				const int a = (int) lane / subsets, s = (int) lane - a * subsets;
 				gather_subset(ws.B, subsets, ws.top[a], s, sp.dim, sub, n);
 				unpack_idx(ws.qidx[ws.top[a]][s], idx, n);
-				if (U8) make_u8_subset(sub, n, sp.dim, S);
-				if (cube_u8) {
+				if (U8) {
+					U8Subset S;
+					make_u8_subset(sub, n, sp.dim, S);
 					CubeTask &t = ws.task[lane];
 					for (int i = 0; i < 16; i++) t.d[i] = i < n ? S.d[i] : 0u;
 					t.idx_q = pack_idx(idx, n);
@@ -302,31 +454,43 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 					t.bits = (uint8_t) sp.bits[0];
 					t.type = (uint8_t) sp.parity;
 					t.all_same = S.all_same ? 1 : 0;
+					t.dim = (uint8_t) sp.dim;
+					t.w_bits_total = (uint8_t) sp.bits[3];
+					t.w_size = (uint8_t) sp.shake_size;
+					t.w_index = t.idx_q;
+					t.w_active = 1;
 				}
 			}
 			__syncwarp();
-			if (cube_u8) cube_phase(T, ws, ntasks, 1, lane);
+			if (U8) {
+				// shake_subset (:709-805): ep_shaker_d, ep_shaker_2_d on the quantiser's indices, and where the former
+				// won, ep_shaker_2_d again on its indices
+				if (cube_u8) cube_phase(T, ws, ntasks, 1, lane);
+				window_phase(T, ws, ntasks, lane);
+				if (cube_u8) {
+					if ((int) lane < ntasks) {
+						CubeTask &t = ws.task[lane];
+						t.w_active = (t.err_o < t.w_err_o) ? 1 : 0;
+						t.w_index = t.best_idx;
+					}
+					__syncwarp();
+					window_phase(T, ws, ntasks, lane);
+				}
+			}
 			if ((int) lane < ntasks) {
 				ShakeOut o;
 				if (!U8) {
 					o.err = shake_subset(T, sp, sub, n, idx, ep);
-				} else if (sp.dim != 3) {
-					o.err = shake_subset_u8(T, sp, S, idx, ep);
+					o.idx = pack_idx(idx, n);
+					o.ep[0] = pack_ep(ep[0]);
+					o.ep[1] = pack_ep(ep[1]);
 				} else {
-					// shake_subset with the cube result already known (:754-805)
 					const CubeTask &t = ws.task[lane];
-					const int clog = t.clog;
-					const real e0 = t.err_o;
-					real e1 = shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], 3);
-					if (e0 < e1) {
-						unpack_idx(t.best_idx, idx, n);
-						e1 = shake_window_u8_any(T, S, idx, ep, sp.shake_size, clog, sp.bits[3], 3);
-					}
-					o.err = e1;
+					o.err = t.w_err_o;
+					o.idx = t.w_best_idx;
+					o.ep[0] = (uint32_t) t.w_best_ep;
+					o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
 				}
-				o.idx = pack_idx(idx, n);
-				o.ep[0] = pack_ep(ep[0]);
-				o.ep[1] = pack_ep(ep[1]);
 				ws.so[lane] = o;
 			}
 			__syncwarp();
@@ -390,23 +554,38 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 					t.bits = (uint8_t) cb;
 					t.type = CART;
 					t.all_same = S.all_same ? 1 : 0;
+					t.dim = 3;
+					t.w_bits_total = (uint8_t) (6 * cb);
+					t.w_size = 6;
 				}
 			}
 			__syncwarp();
-			if (U8) cube_phase(T, ws, ntasks, ntasks <= 8 ? 4 : 2, lane);
+			if (U8) {
+				cube_phase(T, ws, ntasks, ntasks <= 8 ? 4 : 2, lane);
+				if ((int) lane < ntasks) {
+					CubeTask &t = ws.task[lane];
+					t.w_index = t.best_idx;
+					t.w_active = 1;
+				}
+				__syncwarp();
+				window_phase(T, ws, ntasks, lane);
+			}
 			if ((int) lane < ntasks) {
 				const int bits[4] = {cb, cb, cb, 6 * cb};
 				ShakeOut o;
 				if (U8) {
-					unpack_idx(ws.task[lane].best_idx, idx, 16);
-					o.err = shake_window_u8_any(T, S, idx, ep, 6, ib, bits[3], 3);
+					const CubeTask &t = ws.task[lane];
+					o.err = t.w_err_o;
+					o.idx = t.w_best_idx;
+					o.ep[0] = (uint32_t) t.w_best_ep;
+					o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
 				} else {
 					shake_cube(T, blkv, 16, idx, (1 << ib) - 1, bits, CART);
 					o.err = shake_window(T, blkv, 16, idx, ep, 6, (1 << ib) - 1, bits[3], 3);
+					o.idx = pack_idx(idx, 16);
+					o.ep[0] = pack_ep(ep[0]);
+					o.ep[1] = pack_ep(ep[1]);
 				}
-				o.idx = pack_idx(idx, 16);
-				o.ep[0] = pack_ep(ep[0]);
-				o.ep[1] = pack_ep(ep[1]);
 				ws.so[lane] = o;
 			}
 			__syncwarp();

@@ -316,27 +316,146 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 	return err_o;
 }
 
+// ---- ep_shaker_2_d (:703-1053) on packed 8-bit data, cut into its two kinds of independent work -------------
+A7_HD uint64_t pack_ep8(const int ep[2][4]) { // 8 endpoint codes, one byte each: ep[0][0..3] | ep[1][0..3] << 32
+	uint64_t v = 0;
+#pragma unroll
+	for (int j = 0; j < 4; j++) v |= ((uint64_t) (ep[0][j] & 255) << (8 * j)) | ((uint64_t) (ep[1][j] & 255) << (32 + 8 * j));
+	return v;
+}
+A7_HD void unpack_ep8(uint64_t v, int ep[2][4]) {
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		ep[0][j] = (int) ((v >> (8 * j)) & 255u);
+		ep[1][j] = (int) ((v >> (32 + 8 * j)) & 255u);
+	}
+}
+
+// One (q, p) re-indexing (:836-1000): least-squares endpoints, per-channel window search with fixed indices, best
+// parity vector. Returns err_1 (exact integer) and epo_1 (packed).
+template <int CLOG>
+A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, int size, int bits_total, int dim, uint64_t &epo_out) {
+	constexpr int C = 1 << CLOG, Mi_ = C - 1;
+	constexpr int W = C > 8 ? 2 : 1;
+	const int type = bits_total % (2 * dim);
+	const int use_par = type != 0;
+	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
+	int cidx[kMaxEntries];
+	int sq_total[4] = {0, 0, 0, 0}; // sum of squares of the data per channel
+#pragma unroll 1
+	for (int k = 0; k < n; k++) {
+		cidx[k] = (int) ((collapsed >> (4 * k)) & 15u) * q + p;
+#pragma unroll 1
+		for (int j = 0; j < dim; j++) {
+			const int b = (int) ((d[k] >> (8 * j)) & 255u);
+			sq_total[j] += b * b;
+		}
+	}
+	ClusterStats cs;
+	cluster_stats(d, n, cidx, Mi_, dim, cs);
+	real epa[2][4];
+	fit_endpoints_u8(cs, cidx, n, Mi_, dim, epa);
+	int ed[2][2][4], ep2[2][2][2][4];
+	const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
+#pragma unroll 1
+	for (int j = 0; j < dim; j++)
+#pragma unroll 1
+		for (int pp0 = 0; pp0 < rr; pp0++)
+#pragma unroll 1
+			for (int pp1 = 0; pp1 < rr; pp1++) {
+				int lo[2], hi[2];
+#pragma unroll 1
+				for (int i = 0; i < 2; i++) {
+					const int f = endpoint_floor(epa[i][j], mb, use_par, i ? pp1 : pp0);
+					lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
+					hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
+				}
+				int best = INT32_MAX, b1 = 0, b2 = 0;
+#pragma unroll 1
+				for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
+					const int e1 = expand_bits(mb, p1);
+#pragma unroll 1
+					for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
+						uint64_t rv[W];
+						ramp_bytes<CLOG>(e1, expand_bits(mb, p2), rv);
+						// sum_m (rv[cidx[m]] - d[m])^2 == sum d^2 + sum_c rv_c * (cnt_c * rv_c - 2 * S1_c)
+						int t = sq_total[j];
+#pragma unroll
+						for (int c = 0; c < C; c++) {
+							const int r = (int) byte_of(rv[c >> 3], c & 7);
+							t += r * (cs.cnt[c] * r - 2 * cs.sum[c][j]);
+						}
+						if (t < best) { best = t; b1 = p1; b2 = p2; }
+					}
+				}
+				ed[pp0][pp1][j] = best;
+				ep2[pp0][pp1][0][j] = b1;
+				ep2[pp0][pp1][1][j] = b2;
+			}
+	int64_t err_1 = INT64_MAX;
+	int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
+	for (int pn = 0; pn < (1 << type); pn++) {
+		const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
+		int64_t e2 = 0;
+#pragma unroll 1
+		for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
+		if (e2 < err_1) {
+			err_1 = e2;
+#pragma unroll 1
+			for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
+		}
+	}
+	epo_out = pack_ep8(epo_1);
+	return (uint32_t) err_1;
+}
+
+// Re-clustering against chosen endpoints (:1003-1030): packed palette, 4 native instructions per (texel, entry)
+template <int CLOG>
+A7_HDN uint32_t recluster_u8(const uint32_t *d, int n, uint64_t epo, int mb, int dim, uint64_t &idg_out) {
+	constexpr int C = 1 << CLOG;
+	constexpr int W = C > 8 ? 2 : 1;
+	int ep[2][4];
+	unpack_ep8(epo, ep);
+	uint32_t pal[C];
+	{
+		uint64_t rb[4][W];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			rb[j][0] = 0;
+			if (W > 1) rb[j][W - 1] = 0;
+			if (j < dim) ramp_bytes<CLOG>(expand_bits(mb, ep[0][j]), expand_bits(mb, ep[1][j]), rb[j]);
+		}
+#pragma unroll
+		for (int c = 0; c < C; c++)
+			pal[c] = byte_of(rb[0][c >> 3], c & 7) | (byte_of(rb[1][c >> 3], c & 7) << 8) | (byte_of(rb[2][c >> 3], c & 7) << 16) |
+							 (byte_of(rb[3][c >> 3], c & 7) << 24);
+	}
+	uint32_t err_r = 0;
+	uint64_t idg = 0;
+#pragma unroll 1
+	for (int i = 0; i < n; i++) {
+		uint32_t m = 0xffffffffu;
+#pragma unroll
+		for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], d[i]) << 4) | (uint32_t) c);
+		err_r += m >> 4;
+		idg |= (uint64_t) (m & 15u) << (4 * i);
+	}
+	idg_out = idg;
+	return err_r;
+}
+
 // ep_shaker_2_d on packed 8-bit data (dimension 3 or 4). index_io in/out, epo_code out; returns the SSE.
 template <int CLOG>
 A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, int epo_code[2][4], int size, int bits_total, int dim) {
-	constexpr int C = 1 << CLOG, Mi_ = C - 1;
-	constexpr int W = C > 8 ? 2 : 1;
+	constexpr int Mi_ = (1 << CLOG) - 1;
 	const int n = S.n;
 	const int type = bits_total % (2 * dim);
-	const int use_par = type != 0;
 	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
 	const int max_bits[4] = {mb, mb, mb, mb};
 	int index[kMaxEntries];
 #pragma unroll 1
 	for (int k = 0; k < n; k++) index[k] = index_io[k];
-	int sq_total[4] = {0, 0, 0, 0}; // sum of squares of the data per channel
-#pragma unroll 1
-	for (int i = 0; i < n; i++)
-#pragma unroll 1
-		for (int j = 0; j < dim; j++) {
-			const int b = (int) ((S.d[i] >> (8 * j)) & 255u);
-			sq_total[j] += b * b;
-		}
 	real err_o = A7_HUGE;
 	int maxTry = 8, done;
 	do {
@@ -353,104 +472,27 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 			}
 			return err_o;
 		}
+		uint64_t collapsed = 0;
+#pragma unroll 1
+		for (int k = 0; k < n; k++) collapsed |= (uint64_t) (index[k] & 15) << (4 * k);
 		int p0 = -1, q0 = -1;
-		int64_t err_0 = INT64_MAX;
-		int epo_0[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+		uint32_t err_0 = 0xffffffffu;
+		uint64_t epo_0 = 0;
 #pragma unroll 1
 		for (int q = 1; q * Mi <= Mi_; q++)
 #pragma unroll 1
 			for (int p = 0; p <= Mi_ - q * Mi; p++) {
-				int cidx[kMaxEntries];
-#pragma unroll 1
-				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
-				ClusterStats cs;
-				cluster_stats(S.d, n, cidx, Mi_, dim, cs);
-				real epa[2][4];
-				fit_endpoints_u8(cs, cidx, n, Mi_, dim, epa);
-				int ed[2][2][4], ep2[2][2][2][4];
-				const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
-#pragma unroll 1
-				for (int j = 0; j < dim; j++)
-#pragma unroll 1
-					for (int pp0 = 0; pp0 < rr; pp0++)
-#pragma unroll 1
-						for (int pp1 = 0; pp1 < rr; pp1++) {
-							int lo[2], hi[2];
-#pragma unroll 1
-							for (int i = 0; i < 2; i++) {
-								const int f = endpoint_floor(epa[i][j], mb, use_par, i ? pp1 : pp0);
-								lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
-								hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
-							}
-							int best = INT32_MAX, b1 = 0, b2 = 0;
-#pragma unroll 1
-							for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
-								const int e1 = expand_bits(mb, p1);
-#pragma unroll 1
-								for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
-									uint64_t rv[W];
-									ramp_bytes<CLOG>(e1, expand_bits(mb, p2), rv);
-									// sum_m (rv[cidx[m]] - d[m])^2 == sum d^2 + sum_c rv_c * (cnt_c * rv_c - 2 * S1_c)
-									int t = sq_total[j];
-#pragma unroll
-									for (int c = 0; c < C; c++) {
-										const int r = (int) byte_of(rv[c >> 3], c & 7);
-										t += r * (cs.cnt[c] * r - 2 * cs.sum[c][j]);
-									}
-									if (t < best) { best = t; b1 = p1; b2 = p2; }
-								}
-							}
-							ed[pp0][pp1][j] = best;
-							ep2[pp0][pp1][0][j] = b1;
-							ep2[pp0][pp1][1][j] = b2;
-						}
-				int64_t err_1 = INT64_MAX;
-				int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-#pragma unroll 1
-				for (int pn = 0; pn < (1 << type); pn++) {
-					const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
-					int64_t e2 = 0;
-#pragma unroll 1
-					for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
-					if (e2 < err_1) {
-						err_1 = e2;
-#pragma unroll 1
-						for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
-					}
-				}
-				if (err_1 <= err_0) {
+				uint64_t epo_1;
+				const uint32_t err_1 = window_item_u8<CLOG>(S.d, n, collapsed, q, p, size, bits_total, dim, epo_1);
+				if (err_1 <= err_0) { // `<=`: the LAST minimum wins (:994)
 					err_0 = err_1;
 					p0 = p;
 					q0 = q;
-#pragma unroll 1
-					for (int j = 0; j < dim; j++) { epo_0[0][j] = epo_1[0][j]; epo_0[1][j] = epo_1[1][j]; }
+					epo_0 = epo_1;
 				}
 			}
-		// re-cluster against the chosen endpoints: packed palette, 4 native instructions per (texel, entry)
-		uint32_t pal[C];
-		{
-			uint64_t rb[4][W];
-#pragma unroll 1
-			for (int j = 0; j < 4; j++) {
-				rb[j][0] = 0;
-				if (W > 1) rb[j][W - 1] = 0;
-				if (j < dim) ramp_bytes<CLOG>(expand_bits(mb, epo_0[0][j]), expand_bits(mb, epo_0[1][j]), rb[j]);
-			}
-#pragma unroll
-			for (int c = 0; c < C; c++)
-				pal[c] = byte_of(rb[0][c >> 3], c & 7) | (byte_of(rb[1][c >> 3], c & 7) << 8) | (byte_of(rb[2][c >> 3], c & 7) << 16) |
-								 (byte_of(rb[3][c >> 3], c & 7) << 24);
-		}
-		uint32_t err_r = 0;
-		uint64_t idg = 0;
-#pragma unroll 1
-		for (int i = 0; i < n; i++) {
-			uint32_t m = 0xffffffffu;
-#pragma unroll
-			for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], S.d[i]) << 4) | (uint32_t) c);
-			err_r += m >> 4;
-			idg |= (uint64_t) (m & 15u) << (4 * i);
-		}
+		uint64_t idg;
+		const uint32_t err_r = recluster_u8<CLOG>(S.d, n, epo_0, mb, dim, idg);
 		int change = 0;
 #pragma unroll 1
 		for (int k = 0; k < n; k++) change = change || (index[k] * q0 + p0 != (int) ((idg >> (4 * k)) & 15u));
@@ -458,8 +500,7 @@ A7_HDN real shake_window_u8(const Tables &T, const U8Subset &S, int *index_io, i
 		if (better) {
 #pragma unroll 1
 			for (int k = 0; k < n; k++) index_io[k] = index[k] = (int) ((idg >> (4 * k)) & 15u);
-#pragma unroll 1
-			for (int j = 0; j < dim; j++) { epo_code[0][j] = epo_0[0][j]; epo_code[1][j] = epo_0[1][j]; }
+			unpack_ep8(epo_0, epo_code);
 			err_o = (real) err_r;
 		}
 		done = !(change && better);
