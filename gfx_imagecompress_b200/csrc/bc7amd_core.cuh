@@ -152,55 +152,79 @@ A7_HD void sort_order(const real *key, int *order, int n) {
 }
 A7_HD int ilog2(int v) { int c = 0; while (v >>= 1) c++; return c; }
 
-// eigenVector_d (:336-420): dominant eigenvector by repeated squaring, 3 rounds of 8
-A7_HDN void dominant_axis(const real cov[4][4], real axis[4], int dim) {
-	real c[2][4][4];
-#pragma unroll 1
-	for (int i = 0; i < dim; i++)
-#pragma unroll 1
-		for (int j = 0; j < dim; j++) c[0][i][j] = cov[i][j];
-	int l = 0;
+// eigenVector_d (:336-420): dominant eigenvector by repeated squaring, 3 rounds of (normalise by the largest
+// diagonal entry, square 8 times). The covariance is bitwise symmetric and stays so (division by one scalar; a
+// product term c[i][k]*c[k][j] of (i,j) equals the term c[j][k]*c[k][i] of (j,i) and both sums run over k in the
+// same order), so only the upper triangle is computed -- identical bits, two thirds of the work, all in registers.
+template <int DIM> A7_HD void dominant_axis_t(const real cov[4][4], real axis[4]) {
+	real c[DIM][DIM];
+#pragma unroll
+	for (int i = 0; i < DIM; i++)
+#pragma unroll
+		for (int j = 0; j < DIM; j++) c[i][j] = cov[i][j];
 #pragma unroll 1
 	for (int round = 0; round < 3; round++) {
 		real md = 0;
-#pragma unroll 1
-		for (int i = 0; i < dim; i++) md = c[l][i][i] > md ? c[l][i][i] : md;
+#pragma unroll
+		for (int i = 0; i < DIM; i++) md = c[i][i] > md ? c[i][i] : md;
 		if (md <= 0) return;
-#pragma unroll 1
-		for (int i = 0; i < dim; i++)
-#pragma unroll 1
-			for (int j = 0; j < dim; j++) c[l][i][j] /= md;
+#pragma unroll
+		for (int i = 0; i < DIM; i++)
+#pragma unroll
+			for (int j = i; j < DIM; j++) {
+				c[i][j] /= md;
+				c[j][i] = c[i][j];
+			}
 #pragma unroll 1
 		for (int m = 0; m < 8; m++) {
-#pragma unroll 1
-			for (int i = 0; i < dim; i++)
-#pragma unroll 1
-				for (int j = 0; j < dim; j++) {
+			real nx[DIM][DIM];
+#pragma unroll
+			for (int i = 0; i < DIM; i++)
+#pragma unroll
+				for (int j = i; j < DIM; j++) {
 					real t = 0;
-#pragma unroll 1
-					for (int k = 0; k < dim; k++) t += c[l][i][k] * c[l][k][j];
-					c[1 - l][i][j] = t;
+#pragma unroll
+					for (int k = 0; k < DIM; k++) t += c[i][k] * c[k][j];
+					nx[i][j] = t;
 				}
-			l = 1 - l;
+#pragma unroll
+			for (int i = 0; i < DIM; i++)
+#pragma unroll
+				for (int j = i; j < DIM; j++) {
+					c[i][j] = nx[i][j];
+					c[j][i] = nx[i][j];
+				}
 		}
 	}
 	real md = 0;
 	int k = 0;
-#pragma unroll 1
-	for (int i = 0; i < dim; i++) {
-		k = c[l][i][i] > md ? i : k;
-		md = c[l][i][i] > md ? c[l][i][i] : md;
+#pragma unroll
+	for (int i = 0; i < DIM; i++) {
+		k = c[i][i] > md ? i : k;
+		md = c[i][i] > md ? c[i][i] : md;
+	}
+	real row[DIM];
+#pragma unroll
+	for (int i = 0; i < DIM; i++) {
+		row[i] = c[0][i];
+#pragma unroll
+		for (int r = 1; r < DIM; r++)
+			if (k == r) row[i] = c[r][i];
 	}
 	real t = 0;
-#pragma unroll 1
-	for (int i = 0; i < dim; i++) {
-		t += c[l][k][i] * c[l][k][i];
-		axis[i] = c[l][k][i];
+#pragma unroll
+	for (int i = 0; i < DIM; i++) {
+		t += row[i] * row[i];
+		axis[i] = row[i];
 	}
 	t = sqrt(t);
 	if (t <= 0) return;
-#pragma unroll 1
-	for (int i = 0; i < dim; i++) axis[i] /= t;
+#pragma unroll
+	for (int i = 0; i < DIM; i++) axis[i] /= t;
+}
+A7_HDN void dominant_axis(const real cov[4][4], real axis[4], int dim) {
+	if (dim == 3) dominant_axis_t<3>(cov, axis);
+	else dominant_axis_t<4>(cov, axis);
 }
 
 // quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of n scalars (lattice A_n* decoding)
