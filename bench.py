@@ -149,7 +149,7 @@ def cpu_reference_sample(codec: int, size: int, seed: int, budget_s: float, step
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--codec", default="auto", choices=["auto"] + list(CODECS))
@@ -254,7 +254,7 @@ def main():
         step_host()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 2))
     for _ in range(e2e_steps):
         step_host()
     barrier()
