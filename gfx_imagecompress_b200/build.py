@@ -30,7 +30,7 @@ UNITS = [
     ("bc1.cu", ["--fmad=false"]),
     ("bc7rg.cu", ["--fmad=false"]),
     ("bc7amd.cu", ["--fmad=false"]),
-    ("bc6h.cu", []),
+    ("bc6h.cu", ["--fmad=false"]),
     ("image_shim.cpp", []),
 ]
 HAVE = {"bc1.cu": "B200IC_HAVE_BC1", "bc7rg.cu": "B200IC_HAVE_BC7RG", "bc7amd.cu": "B200IC_HAVE_BC7AMD",

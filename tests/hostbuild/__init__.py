@@ -34,6 +34,8 @@ def load():
                        ["-I" + _CSRC, "-I" + os.path.join(_ROOT, "include"), "-o", _LIB, os.path.join(_HERE, "hostbuild.cpp")], check=True)
     L = C.CDLL(_LIB)
     L.hb_bc7rg_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+    if hasattr(L, "hb_bc6h_blocks"):
+        L.hb_bc6h_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     if hasattr(L, "hb_bc1_blocks"):
         L.hb_bc1_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
     if hasattr(L, "hb_bc7amd_blocks"):
@@ -61,4 +63,11 @@ def bc1_blocks(L, blocks_f32: np.ndarray, alpha_threshold: float = 128 / 255.0, 
     b = np.ascontiguousarray(blocks_f32, np.float32).reshape(-1, 64)
     out = np.zeros((len(b), 8), np.uint8)
     L.hb_bc1_blocks(b.ctypes.data, len(b), alpha_threshold, steps, out.ctypes.data)
+    return out
+
+
+def bc6h_blocks(L, blocks_f32: np.ndarray, is_signed: bool = False) -> np.ndarray:
+    b = np.ascontiguousarray(blocks_f32, np.float32).reshape(-1, 64)
+    out = np.zeros((len(b), 16), np.uint8)
+    L.hb_bc6h_blocks(b.ctypes.data, len(b), int(is_signed), out.ctypes.data)
     return out

@@ -17,8 +17,21 @@
 #ifdef HB_BC1
 #include "bc1_core.cuh"
 #endif
+#ifdef HB_BC6H
+#include "bc6h_core.cuh"
+#endif
 
 extern "C" {
+#ifdef HB_BC6H
+// in: nblocks x 64 floats (RGBA, linear HDR); out: nblocks x 16 bytes
+void hb_bc6h_blocks(const float *in, uint64_t nblocks, int is_signed, uint8_t *out) {
+	for (uint64_t b = 0; b < nblocks; b++) {
+		uint64_t w[2];
+		b200ic::bc6::encode_block_serial(in + b * 64, is_signed != 0, w);
+		memcpy(out + b * 16, w, 16);
+	}
+}
+#endif
 #ifdef HB_BC1
 // in: nblocks x 64 floats RGBA 0..1; out: nblocks x 8 bytes
 void hb_bc1_blocks(const float *in, uint64_t nblocks, float alpha_threshold, int steps, uint8_t *out) {
