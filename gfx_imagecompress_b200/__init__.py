@@ -7,7 +7,7 @@ There is no CPU fallback: importing works without a GPU, encoding raises.
 """
 from .api import (  # noqa: F401
     BC1, BC4, BC5, BC6H, BC7_AMD, BC7_RG, BLOCK_BYTES, B200Error, Opts, Image, library, load_library,
-    encode_host, encode_device, encode_blocks, launch_count, init, codec_available,
+    encode_host, encode_device, encode_blocks, encode_batch_device, plan_shards, launch_count, init, codec_available,
     Image_CompressAMDBC1, Image_CompressAMDBC4, Image_CompressAMDBC5, Image_CompressAMDBC6H, Image_CompressAMDBC7,
     Image_CompressRichGel999BC7, ImageCompress_Compress,
     Image_CompressAMDAlphaSingleModeBlock, Image_CompressAMDBC1Block, Image_CompressAMDMultiModeLDRBlock,

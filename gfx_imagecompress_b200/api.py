@@ -86,6 +86,10 @@ def load_library(path: str | None = None):
     L.b200ic_encode_host.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200ic_encode_blocks.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.b200ic_plan_shards.restype = C.c_uint64
+    L.b200ic_plan_shards.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                     C.c_uint64]
+    L.b200ic_encode_batch_device.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     for name in ("Image_CompressAMDBC1", "Image_CompressAMDBC2", "Image_CompressAMDBC3", "Image_CompressAMDBC4",
                  "Image_CompressAMDBC5", "Image_CompressAMDBC6H", "Image_CompressAMDBC7", "Image_CompressRichGel999BC7",
                  "ImageCompress_Compress"):
@@ -191,6 +195,54 @@ def encode_blocks(codec: int, blocks: np.ndarray, fmt: int, opts: Opts | None = 
     _check(L.b200ic_encode_blocks(codec, blocks.ctypes.data, fmt, n, C.byref(opts) if opts is not None else None,
                                   out.ctypes.data), "b200ic_encode_blocks")
     return out
+
+
+class ImageDesc(C.Structure):
+    """b200ic_image_desc"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("format", C.c_int32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("reserved", C.c_uint32), ("row_pitch_bytes", C.c_uint64)]
+
+
+class Shard(C.Structure):
+    """b200ic_shard: block-rows [row0, row1) of image `image`"""
+    _fields_ = [("image", C.c_uint32), ("row0", C.c_uint32), ("row1", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def plan_shards(dims, world: int, rank: int, chunk_rows: int = 0):
+    """b200ic_plan_shards: dims = [(width, height), ...] -> [(image, row0, row1), ...] of `rank` (host only, no GPU)."""
+    L = library()
+    n = len(dims)
+    w = (C.c_uint32 * max(n, 1))(*[d[0] for d in dims])
+    h = (C.c_uint32 * max(n, 1))(*[d[1] for d in dims])
+    count = L.b200ic_plan_shards(w, h, n, chunk_rows, world, rank, None, 0)
+    out = (Shard * max(count, 1))()
+    L.b200ic_plan_shards(w, h, n, chunk_rows, world, rank, out, count)
+    return [(out[i].image, out[i].row0, out[i].row1) for i in range(count)]
+
+
+def encode_batch_device(codec: int, images, fmt: int, outs=None, shards=None, opts: Opts | None = None, stream=None):
+    """b200ic_encode_batch_device: `images` = CUDA torch tensors (H, W, C) in `fmt`, one per texture / mip level; `outs` =
+    matching (nblocks, blockBytes) uint8 tensors (allocated if None); `shards` = [(image, row0, row1)] or None (whole
+    images). Asynchronous on torch's current stream."""
+    import torch
+    L = library()
+    if outs is None:
+        outs = [torch.empty((((t.shape[0] + 3) // 4) * ((t.shape[1] + 3) // 4), BLOCK_BYTES[codec]), dtype=torch.uint8,
+                            device=t.device) for t in images]
+    descs = (ImageDesc * max(len(images), 1))()
+    for i, (t, o) in enumerate(zip(images, outs)):
+        assert t.is_cuda and t.is_contiguous() and o.is_cuda and o.is_contiguous()
+        descs[i] = ImageDesc(t.data_ptr(), o.data_ptr(), fmt, t.shape[1], t.shape[0], 0, 0)
+    sh = None
+    if shards is not None:
+        sh = (Shard * max(len(shards), 1))(*[Shard(i, a, b, 0) for i, a, b in shards])
+    dev = images[0].device if images else None
+    st = stream if stream is not None else (torch.cuda.current_stream(dev).cuda_stream if dev is not None else None)
+    with torch.cuda.device(dev):
+        rc = L.b200ic_encode_batch_device(codec, descs, len(images), sh, len(shards) if shards is not None else 0,
+                                          C.byref(opts) if opts is not None else None, st)
+    _check(rc, "b200ic_encode_batch_device")
+    return outs
 
 
 # ---- the reference-facing image API ----------------------------------------------------------------------

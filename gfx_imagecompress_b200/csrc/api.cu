@@ -2,6 +2,7 @@
 // host-buffer path (block-row chunks pipelined H2D -> kernel -> D2H over a small ring of streams).
 // No CPU fallback exists: without a usable CUDA device every encode call fails loudly.
 #include "kernels.h"
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -77,12 +78,15 @@ struct HostCtx {
 	size_t in_cap[kStreams] = {};
 	size_t out_cap[kStreams] = {};
 	bool ready = false;
+	cudaEvent_t fork = nullptr, join[kStreams] = {};
 
 	int ensure(int dev) {
 		if (ready && dev == device) return 0;
 		release();
 		device = dev;
 		for (int i = 0; i < kStreams; i++) B200IC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "stream create");
+		B200IC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "event create");
+		for (int i = 0; i < kStreams; i++) B200IC_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming), "event create");
 		ready = true;
 		return 0;
 	}
@@ -109,10 +113,14 @@ struct HostCtx {
 			if (streams[i]) cudaStreamDestroy(streams[i]);
 			if (d_in[i]) cudaFree(d_in[i]);
 			if (d_out[i]) cudaFree(d_out[i]);
+			if (join[i]) cudaEventDestroy(join[i]);
+			join[i] = nullptr;
 			streams[i] = nullptr;
 			d_in[i] = d_out[i] = nullptr;
 			in_cap[i] = out_cap[i] = 0;
 		}
+		if (fork) cudaEventDestroy(fork);
+		fork = nullptr;
 		ready = false;
 	}
 	~HostCtx() { /* process teardown: the driver reclaims everything */ }
@@ -354,6 +362,98 @@ int b200ic_encode_blocks(int codec, const void *h_blocks, int format, uint64_t n
 	B200IC_CUDA(cudaMemcpyAsync(h_dst, t_ctx.d_out[0], (size_t) nblocks * bb, cudaMemcpyDeviceToHost, st), "D2H copy");
 	B200IC_CUDA(cudaStreamSynchronize(st), "encode blocks");
 	return 0;
+}
+
+uint64_t b200ic_plan_shards(const uint32_t *widths, const uint32_t *heights, uint64_t n_images, uint32_t chunk_rows, uint32_t world,
+														uint32_t rank, b200ic_shard *out, uint64_t cap) {
+	if (!widths || !heights || world == 0 || rank >= world) return 0;
+	if (chunk_rows == 0) chunk_rows = 64;
+	struct Chunk {
+		uint64_t blocks;
+		uint32_t image, row0, row1;
+	};
+	std::vector<Chunk> chunks;
+	for (uint64_t i = 0; i < n_images; i++) {
+		const uint32_t bx = (widths[i] + 3) / 4, by = (heights[i] + 3) / 4;
+		for (uint32_t r = 0; r < by; r += chunk_rows) {
+			const uint32_t r1 = r + chunk_rows < by ? r + chunk_rows : by;
+			chunks.push_back({(uint64_t) bx * (r1 - r), (uint32_t) i, r, r1});
+		}
+	}
+	// largest first; equal sizes keep (image, row) order so that the plan is a pure function of the dimensions
+	std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &b) { return a.blocks > b.blocks; });
+	std::vector<uint64_t> load(world, 0);
+	std::vector<Chunk> mine;
+	for (const Chunk &c : chunks) {
+		uint32_t best = 0;
+		for (uint32_t r = 1; r < world; r++)
+			if (load[r] < load[best]) best = r;
+		load[best] += c.blocks;
+		if (best == rank) mine.push_back(c);
+	}
+	std::sort(mine.begin(), mine.end(), [](const Chunk &a, const Chunk &b) { return a.image != b.image ? a.image < b.image : a.row0 < b.row0; });
+	uint64_t n = 0;
+	b200ic_shard cur = {0, 0, 0, 0};
+	bool have = false;
+	auto flush = [&]() {
+		if (!have) return;
+		if (out && n < cap) out[n] = cur;
+		n++;
+	};
+	for (const Chunk &c : mine) {
+		if (have && cur.image == c.image && cur.row1 == c.row0) {
+			cur.row1 = c.row1;
+			continue;
+		}
+		flush();
+		cur = {c.image, c.row0, c.row1, 0};
+		have = true;
+	}
+	flush();
+	return n;
+}
+
+int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint64_t n_images, const b200ic_shard *shards,
+															 uint64_t n_shards, const b200ic_opts *opts, void *stream) {
+	t_error.clear();
+	if (!images && n_images) return fail("null image table");
+	const uint32_t bb = block_bytes(codec);
+	if (bb == 0) return fail("unsupported codec");
+	if (ensure_device()) return -1;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (t_ctx.ensure(dev)) return -1;
+	const uint64_t count = shards ? n_shards : n_images;
+	if (count == 0) return 0;
+	cudaStream_t user = static_cast<cudaStream_t>(stream);
+	const int ring = HostCtx::kStreams;
+	B200IC_CUDA(cudaEventRecord(t_ctx.fork, user), "fork");
+	for (int i = 0; i < ring; i++) B200IC_CUDA(cudaStreamWaitEvent(t_ctx.streams[i], t_ctx.fork, 0), "fork");
+	int rc = 0;
+	for (uint64_t k = 0; k < count && rc == 0; k++) {
+		b200ic_shard sh;
+		if (shards) sh = shards[k];
+		else sh = {(uint32_t) k, 0, 0xffffffffu, 0};
+		if (sh.image >= n_images) { rc = fail("shard names an image outside the table"); break; }
+		const b200ic_image_desc &im = images[sh.image];
+		const uint32_t tb = texel_bytes(im.format);
+		if (tb == 0) { rc = fail("unsupported source format"); break; }
+		if (im.width == 0 || im.height == 0) { rc = fail("empty image"); break; }
+		const uint32_t blocks_x = (im.width + 3) / 4, blocks_y = (im.height + 3) / 4;
+		const uint32_t r0 = sh.row0, r1 = sh.row1 < blocks_y ? sh.row1 : blocks_y;
+		if (r0 >= r1) continue;
+		const uint64_t pitch = im.row_pitch_bytes ? im.row_pitch_bytes : (uint64_t) im.width * tb;
+		const uint32_t y0 = r0 * 4, y1 = r1 * 4 < im.height ? r1 * 4 : im.height;
+		const uint8_t *src = static_cast<const uint8_t *>(im.src) + (uint64_t) y0 * pitch;
+		uint8_t *dst = static_cast<uint8_t *>(im.dst) + (uint64_t) r0 * blocks_x * bb;
+		// big shards fill the GPU on their own and go to the caller's order on stream 0; small ones (low mips) overlap
+		rc = b200ic_encode_device(codec, src, im.format, im.width, y1 - y0, pitch, 0, 1, opts, dst, t_ctx.streams[k % ring]);
+	}
+	for (int i = 0; i < ring; i++) {
+		cudaEventRecord(t_ctx.join[i], t_ctx.streams[i]);
+		cudaStreamWaitEvent(user, t_ctx.join[i], 0);
+	}
+	return rc;
 }
 
 } // extern "C"

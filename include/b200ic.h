@@ -112,6 +112,36 @@ B200IC_API int b200ic_encode_host(int codec, const void *h_src, int format, uint
 B200IC_API int b200ic_encode_blocks(int codec, const void *h_blocks, int format, uint64_t nblocks,
 																		const b200ic_opts *opts, void *h_dst);
 
+/* ---- batches and multi-GPU sharding (BASELINE config[4]: texture batches with mip chains, block-row sharded) -------
+ * The reference compresses one image per call and never walks mip chains: callers loop over
+ * textures and levels (reference src/amd_bc7_compressor.cpp:25-80 once per level).  Here the loop is a batch. */
+typedef struct b200ic_image_desc {
+	const void *src;             /* device pointer, `height` rows of `row_pitch_bytes` (0 = tightly packed) */
+	void *dst;                   /* device pointer, blocksY x blocksX blocks, row-major */
+	int32_t format;              /* b200ic_format (texel formats only) */
+	uint32_t width, height;
+	uint32_t reserved;
+	uint64_t row_pitch_bytes;
+} b200ic_image_desc;
+
+/* A shard = block-rows [row0, row1) of image `image`. */
+typedef struct b200ic_shard {
+	uint32_t image, row0, row1, reserved;
+} b200ic_shard;
+
+/* Deterministic partition of the block-rows of `n_images` images over `world` ranks (every rank computes the same
+ * plan, no communication): images are cut into chunks of at most `chunk_rows` block-rows (0 = 64), the chunks are
+ * dealt largest-first to the least loaded rank (ties to the lowest rank), and each rank's chunks are returned sorted
+ * by (image, row0) with adjacent ranges merged.  Blocks are independent, so the encode needs no halo and no
+ * collective.  Writes at most `cap` shards of `rank` to `out` and returns how many it has.  Host-only. */
+B200IC_API uint64_t b200ic_plan_shards(const uint32_t *widths, const uint32_t *heights, uint64_t n_images, uint32_t chunk_rows,
+																			 uint32_t world, uint32_t rank, b200ic_shard *out, uint64_t cap);
+
+/* Encodes `n_shards` shards (or, with shards == NULL, every image whole) of device-resident images.  The launches are
+ * spread over internal streams forked from / joined to `stream`, so small mip levels overlap.  Asynchronous. */
+B200IC_API int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint64_t n_images,
+																					const b200ic_shard *shards, uint64_t n_shards, const b200ic_opts *opts, void *stream);
+
 /* Number of kernel launches issued by this library since b200ic_init (for bench.py's gpu_launches). */
 B200IC_API uint64_t b200ic_launch_count(void);
 
