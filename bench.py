@@ -146,6 +146,98 @@ def cpu_reference_sample(codec: int, size: int, seed: int, budget_s: float, step
                             f"{dt:.2f} s per pass, unmodified reference via oracle/_ref, {threads} host threads over row strips"}
 
 
+def bench_batch(args, codec, cname, rank, local_rank, world):
+    """BASELINE config[4]: a batch of RGBA8 textures with full box-filtered mip chains, BC7, block-row sharded over the
+    ranks by b200ic_plan_shards (strong scaling: the batch is fixed, each rank encodes its shards; no data-path
+    collective, the gather of the blocks is outside the timed region)."""
+    import torch
+    import torch.distributed as dist
+    import gfx_imagecompress_b200 as g
+    from gfx_imagecompress_b200 import sharded, synth
+    if args.impl == "reference":
+        if rank == 0:
+            mpix, info = cpu_reference_sample(codec, args.tex_size, 100, args.cpu_budget, max(1, args.steps))
+            print(json.dumps({"impl": "reference", "metric": f"{cname.upper()} Mpix/s, texture batch", "value": mpix, "unit": "Mpix/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "data": "synthetic", "cpu_baseline": info,
+                              "config": {"workload": f"top level of one {args.tex_size}^2 texture (sample)"},
+                              "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    g.load_library()
+    g.init(local_rank)
+    unique = 4
+    chains = []
+    for u in range(unique):
+        top = torch.from_numpy(synth.rgba8_gradnoise(args.tex_size, args.tex_size, 100 + u, "lefthalf")).to(dev)
+        chains.append(sharded.box_mips(top))
+    images = [lvl for t in range(args.textures) for lvl in chains[t % unique]]
+    dims = [(int(t.shape[1]), int(t.shape[0])) for t in images]
+    mine = g.plan_shards(dims, world, rank)
+    bb = g.BLOCK_BYTES[codec]
+    # outputs only for the images this rank touches
+    touched = sorted({i for i, _, _ in mine})
+    outs = [None] * len(images)
+    dummy = torch.empty((1, bb), dtype=torch.uint8, device=dev)
+    for i in range(len(images)):
+        outs[i] = dummy
+    for i in touched:
+        outs[i] = torch.empty((((dims[i][0] + 3) // 4) * ((dims[i][1] + 3) // 4), bb), dtype=torch.uint8, device=dev)
+    my_blocks = sum(((dims[i][0] + 3) // 4) * (b - a) for i, a, b in mine)
+    total_pix = sum(w * h for w, h in dims)
+
+    def step():
+        g.encode_batch_device(codec, images, synth.FMT_RGBA8, outs=outs, shards=mine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3) if codec != 7 else 1):
+        step()
+    barrier()
+    n0 = g.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = g.launch_count() - n0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    if rank == 0:
+        peaks, how = _peaks()
+        value = total_pix / 1e6 * args.steps / (total_ms / 1e3)
+        alg = total_pix * 4 + sum(((w + 3) // 4) * ((h + 3) // 4) for w, h in dims) * bb
+        achieved = alg * args.steps / (total_ms / 1e3) / 1e9
+        print(json.dumps({
+            "metric": f"{cname.upper()} Mpix/s, batch of {args.textures} x {args.tex_size}^2 RGBA8 textures with full mip chains",
+            "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if codec == 7 else "f32", "data": f"synthetic ({unique} unique textures cycled)",
+            "config": {"workload": f"{cname} encode of {args.textures} textures x {len(chains[0])} mip levels, block-row sharded "
+                                   f"over {world} rank(s) by b200ic_plan_shards (BASELINE config[4] shape)", "codec": cname,
+                       "textures": args.textures, "tex_size": args.tex_size, "levels": len(chains[0]),
+                       "rank0_shards": len(mine), "rank0_blocks": my_blocks,
+                       "l2_policy": "distinct outputs per texture; inputs cycle over 4 x 21 MiB chains"},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": how, "kernel": f"{cname}_kernel"}}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +248,11 @@ def main():
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU reference work for cpu_baseline")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="image", choices=["image", "batch"],
+                    help="image: one --size^2 image per rank per step (headline); batch: --textures x (--tex-size^2 + full mip "
+                         "chain), block-row sharded over the ranks (BASELINE config[4])")
+    ap.add_argument("--textures", type=int, default=256)
+    ap.add_argument("--tex-size", type=int, default=2048)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -169,6 +266,8 @@ def main():
     else:
         codec = CODECS[args.codec]
     cname = {v: k for k, v in CODECS.items()}[codec]
+    if args.workload == "batch":
+        return bench_batch(args, codec, cname, rank, local_rank, world)
     size = args.size
     wl = workload(codec, size)
     metric = f"{cname.upper()} Mpix/s at {size}^2 {wl['name'].split()[-1]}"
