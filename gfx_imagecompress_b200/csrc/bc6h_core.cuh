@@ -47,6 +47,13 @@ namespace b200ic {
 namespace bc6 {
 
 constexpr int kMaxEntries = 16;
+constexpr int kQuantMaxTry = 4000; // optQuantAnD_f maxTry at quality 1 (src/amd_hdr_encode.cpp:1439)
+#ifndef H6_STATS_IT
+#define H6_STATS_IT(it)
+#define H6_STATS_F()
+#define H6_STATS_G()
+#define H6_STATS_REPLAY()
+#endif
 
 // BPTC two-subset shapes 0..31 (bit i = subset of texel i) and their anchor texels: format specification
 H6_CONST uint16_t kShape[32] = {0xcccc, 0x8888, 0xeeee, 0xecc8, 0xc880, 0xfeec, 0xfec8, 0xec80, 0xc800, 0xffec, 0xfe80,
@@ -277,98 +284,103 @@ H6_HDN float quantise_subset_f(const float data[][4], int n, int clusters, int *
 		for (int i = 0; i < 3; i++) p += cen[k][i] * dir[i];
 		proj[k] = p;
 	}
+	// The iteration of the reference (:1494-1575). Both steps are pure functions of the index vector -- refit+reassign F and
+	// the lattice quantiser G of the refit's projections -- so the state is one packed word `cur`, F / G are memoised on
+	// it, and once the state after G repeats one of the last 8 states with try_two unchanged (or already negative) the
+	// remaining iterations are periodic with a convergence test that keeps failing: the state after iteration 3999 is
+	// read from the history (see bc7amd_core.cuh quantise_subset; maxTry is 4000 here, so this is most of the saving).
 	uint64_t memo_key[4], memo_f[4], memo_g[4];
 	int memo_gvalid[4] = {0, 0, 0, 0}, memo_n = 0, memo_next = 0;
-	uint64_t first = 0;
+	constexpr int kHist = 8;
+	uint64_t hist[kHist];
+	int hist_try[kHist];
+	uint64_t first = 0, cur = 0;
 	int try_two = 50;
 	float s, t;
+	H6_STATS_G();
+	lattice_quantise_f(proj, clusters, n, index); // iteration 0
 #pragma unroll 1
-	for (int it = 0; it < 4000; it++) {
+	for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
+	int it = 1;
+#pragma unroll 1
+	for (; it < kQuantMaxTry; it++) {
 		int last = -1;
-		bool have_proj = (it == 0);
-		if (it) {
-			int done;
-			do {
-				uint64_t a = 0;
+		bool have_proj = false;
+		int done;
+		do {
+			const uint64_t a = cur;
+			int slot = -1;
 #pragma unroll 1
-				for (int k = 0; k < n; k++) a |= (uint64_t) (index[k] & 15) << (4 * k);
-				int slot = -1;
+			for (int m = 0; m < memo_n; m++)
+				if (memo_key[m] == a) slot = m;
+			uint64_t b;
+			if (slot >= 0) {
+				H6_STATS_REPLAY();
+				b = memo_f[slot];
+				have_proj = false;
+			} else {
+				H6_STATS_F();
+				float q = 0;
+				s = t = 0;
 #pragma unroll 1
-				for (int m = 0; m < memo_n; m++)
-					if (memo_key[m] == a) slot = m;
-				uint64_t b;
-				if (slot >= 0) {
-					b = memo_f[slot];
-#pragma unroll 1
-					for (int k = 0; k < n; k++) index[k] = (int) ((b >> (4 * k)) & 15u);
-					have_proj = false;
-				} else {
-					float q = 0;
-					s = t = 0;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) {
-						s += (float) index[k];
-						t += (float) (index[k] * index[k]);
-					}
-#pragma unroll 1
-					for (int j = 0; j < 3; j++) {
-						float d = 0;
-#pragma unroll 1
-						for (int k = 0; k < n; k++) d += cen[k][j] * (float) index[k];
-						dir[j] = d;
-						q += d * d;
-					}
-					s /= (float) n;
-					t = t - s * s * (float) n;
-					t = (t == 0.0f ? 0.0f : 1.0f / t);
-					q = sqrtf(q);
-					t *= q;
-					if (q != 0)
-#pragma unroll 1
-						for (int j = 0; j < 3; j++) dir[j] /= q;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) {
-						float p = 0;
-#pragma unroll 1
-						for (int i = 0; i < 3; i++) p += cen[k][i] * dir[i];
-						proj[k] = p;
-					}
-					// boundaries (k + 0.5 - s) * t are evaluated in double by the reference's mixed expression (:1549);
-					// they are non-decreasing in k, so the running-k walk over sorted projections == counting
-					double bound[15];
-#pragma unroll 1
-					for (int k = 0; k < clusters - 1; k++) bound[k] = ((double) k + 0.5 - (double) s) * (double) t;
-					b = 0;
-#pragma unroll 1
-					for (int j = 0; j < n; j++) {
-						const double pj = (double) proj[j];
-						int k = 0;
-#pragma unroll 1
-						for (int c = 0; c < clusters - 1; c++) k += (pj > bound[c]) ? 1 : 0;
-						index[j] = k;
-						b |= (uint64_t) k << (4 * j);
-					}
-					slot = memo_next;
-					memo_next = (memo_next + 1) & 3;
-					memo_n = memo_n < 4 ? memo_n + 1 : 4;
-					memo_key[slot] = a;
-					memo_f[slot] = b;
-					memo_gvalid[slot] = 0;
-					have_proj = true;
+				for (int k = 0; k < n; k++) {
+					index[k] = (int) ((a >> (4 * k)) & 15u);
+					s += (float) index[k];
+					t += (float) (index[k] * index[k]);
 				}
-				done = (b == a);
-				last = slot;
-			} while (!done && try_two--);
-			uint64_t cur = 0;
 #pragma unroll 1
-			for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
-			if (it == 1) first = cur;
-			else if (first == cur) break;
-		}
-		if (last >= 0 && memo_gvalid[last]) {
-			const uint64_t g = memo_g[last];
+				for (int j = 0; j < 3; j++) {
+					float d = 0;
 #pragma unroll 1
-			for (int k = 0; k < n; k++) index[k] = (int) ((g >> (4 * k)) & 15u);
+					for (int k = 0; k < n; k++) d += cen[k][j] * (float) index[k];
+					dir[j] = d;
+					q += d * d;
+				}
+				s /= (float) n;
+				t = t - s * s * (float) n;
+				t = (t == 0.0f ? 0.0f : 1.0f / t);
+				q = sqrtf(q);
+				t *= q;
+				if (q != 0)
+#pragma unroll 1
+					for (int j = 0; j < 3; j++) dir[j] /= q;
+#pragma unroll 1
+				for (int k = 0; k < n; k++) {
+					float p = 0;
+#pragma unroll 1
+					for (int i = 0; i < 3; i++) p += cen[k][i] * dir[i];
+					proj[k] = p;
+				}
+				// boundaries (k + 0.5 - s) * t are evaluated in double by the reference's mixed expression (:1549);
+				// they are non-decreasing in k, so the running-k walk over sorted projections == counting
+				double bound[15];
+#pragma unroll 1
+				for (int k = 0; k < clusters - 1; k++) bound[k] = ((double) k + 0.5 - (double) s) * (double) t;
+				b = 0;
+#pragma unroll 1
+				for (int j = 0; j < n; j++) {
+					const double pj = (double) proj[j];
+					int k = 0;
+#pragma unroll 1
+					for (int c = 0; c < clusters - 1; c++) k += (pj > bound[c]) ? 1 : 0;
+					b |= (uint64_t) k << (4 * j);
+				}
+				slot = memo_next;
+				memo_next = (memo_next + 1) & 3;
+				memo_n = memo_n < 4 ? memo_n + 1 : 4;
+				memo_key[slot] = a;
+				memo_f[slot] = b;
+				memo_gvalid[slot] = 0;
+				have_proj = true;
+			}
+			cur = b;
+			done = (b == a);
+			last = slot;
+		} while (!done && try_two--);
+		if (it == 1) first = cur;
+		else if (first == cur) { H6_STATS_IT(it); break; }
+		if (memo_gvalid[last]) {
+			cur = memo_g[last];
 		} else {
 			if (!have_proj) {
 				const uint64_t a = memo_key[last];
@@ -393,16 +405,34 @@ H6_HDN float quantise_subset_f(const float data[][4], int n, int clusters, int *
 					proj[k] = p;
 				}
 			}
+			H6_STATS_G();
 			lattice_quantise_f(proj, clusters, n, index);
-			if (last >= 0) {
-				uint64_t g = 0;
+			cur = 0;
 #pragma unroll 1
-				for (int k = 0; k < n; k++) g |= (uint64_t) (index[k] & 15) << (4 * k);
-				memo_g[last] = g;
-				memo_gvalid[last] = 1;
+			for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
+			memo_g[last] = cur;
+			memo_gvalid[last] = 1;
+		}
+		if (it >= 2) {
+			int period = 0;
+#pragma unroll 1
+			for (int pd = 1; pd <= kHist && pd <= it - 1; pd++) {
+				const int h = (it + 1 - pd) & (kHist - 1);
+				if (hist[h] == cur && (hist_try[h] == try_two || hist_try[h] < 0)) { period = pd; break; }
+			}
+			if (period) {
+				const int r = (kQuantMaxTry - 1 - it) % period;
+				cur = hist[(it + 1 - period + r) & (kHist - 1)];
+				H6_STATS_IT(kQuantMaxTry + 1);
+				break;
 			}
 		}
+		hist[(it + 1) & (kHist - 1)] = cur;
+		hist_try[(it + 1) & (kHist - 1)] = try_two;
+		if (it == kQuantMaxTry - 1) { H6_STATS_IT(kQuantMaxTry); }
 	}
+#pragma unroll 1
+	for (int k = 0; k < n; k++) index[k] = (int) ((cur >> (4 * k)) & 15u);
 	s = t = 0;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {

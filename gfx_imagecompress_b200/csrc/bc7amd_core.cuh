@@ -47,9 +47,13 @@ typedef double real;
 #define A7_HUGE DBL_MAX
 #ifndef A7_STATS_IT
 #define A7_STATS_IT(it)
+#define A7_STATS_F()
+#define A7_STATS_G()
+#define A7_STATS_REPLAY()
 #endif
 
 constexpr int kMaxEntries = 16;
+constexpr int kQuantMaxTry = 200; // optQuantAnD_d maxTry (:1876)
 
 // ---- mode description (bti[], src/amd_bc7_body.cpp:84-94) ---------------------------------------------
 enum Parity { CART = 0, SAME_PAR = 1, BCC = 2 };
@@ -318,103 +322,108 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 	}
 	// The loop below is the reference's (:1911-2007), including its quirks: the convergence test compares against
 	// the indices of iteration 1 (the `index_[j]=index_[j]` no-op, :1997), so an assignment that oscillates never
-	// "converges" and runs all 200 iterations (about 1.3 % of the calls, 100x the cost of the rest). Both steps of
-	// an iteration are PURE functions of the current index vector -- refit+reassign F(index) and the lattice
-	// quantiser G(projection(index)) -- so they are memoised on the packed index vector: an oscillating call
-	// replays the reference's control flow exactly (try_two countdown included) at a few compares per iteration.
+	// "converges" and runs all 200 iterations (0.3 .. 1.4 % of the calls, 100x the cost of the rest).  Both steps of an
+	// iteration are PURE functions of the current index vector -- refit+reassign F(index) and the lattice quantiser
+	// G(projection(index)) -- so
+	//   * the state is carried as one packed 64-bit word `cur` (4 bits per entry) and F / G are memoised on it: a replayed
+	//     step costs a few compares;
+	//   * an iteration is a pure function of (cur, try_two): once the state after G repeats one of the last 8 states
+	//     with try_two unchanged (or already negative: `try_two--` then never cuts a refit chain again) the remaining
+	//     iterations are periodic and no iteration of the period passed the convergence test, so the final state is
+	//     read from the history instead of being replayed (kHist covers every period seen; longer ones just replay).
 	uint64_t memo_key[4], memo_f[4], memo_g[4];
 	int memo_gvalid[4] = {0, 0, 0, 0}, memo_n = 0, memo_next = 0;
-	uint64_t first = 0;
+	constexpr int kHist = 8;
+	uint64_t hist[kHist];
+	int hist_try[kHist];
+	uint64_t first = 0, cur = 0;
 	int try_two = 50;
 	real s;
+	lattice_quantise(proj, clusters, n, index); // iteration 0
+	A7_STATS_G();
 #pragma unroll 1
-	for (int it = 0; it < 200; it++) {
+	for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
+	int it = 1;
+#pragma unroll 1
+	for (; it < kQuantMaxTry; it++) {
 		int last = -1;
-		bool have_proj = (it == 0);
-		if (it) {
-			int done;
-			do {
-				uint64_t a = 0;
+		bool have_proj = false;
+		int done;
+		do {
+			const uint64_t a = cur;
+			int slot = -1;
 #pragma unroll 1
-				for (int k = 0; k < n; k++) a |= (uint64_t) (index[k] & 15) << (4 * k);
-				int slot = -1;
+			for (int m = 0; m < memo_n; m++)
+				if (memo_key[m] == a) slot = m;
+			uint64_t b;
+			if (slot >= 0) {
+				A7_STATS_REPLAY();
+				b = memo_f[slot];
+				have_proj = false;
+			} else {
+				A7_STATS_F();
+				real q = 0;
+				s = t = 0;
 #pragma unroll 1
-				for (int m = 0; m < memo_n; m++)
-					if (memo_key[m] == a) slot = m;
-				uint64_t b;
-				if (slot >= 0) {
-					b = memo_f[slot];
-#pragma unroll 1
-					for (int k = 0; k < n; k++) index[k] = (int) ((b >> (4 * k)) & 15u);
-					have_proj = false;
-				} else {
-					real q = 0;
-					s = t = 0;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) {
-						s += index[k];
-						t += index[k] * index[k];
-					}
-#pragma unroll 1
-					for (int j = 0; j < dim; j++) {
-						real d = 0;
-#pragma unroll 1
-						for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
-						dir[j] = d;
-						q += d * d;
-					}
-					s /= (real) n;
-					t = t - s * s * (real) n;
-					t = (t == 0 ? 0. : 1 / t);
-					q = sqrt(q);
-					t *= q;
-					if (q != 0)
-#pragma unroll 1
-						for (int j = 0; j < dim; j++) dir[j] /= q;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) {
-						real p = 0;
-#pragma unroll 1
-						for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
-						proj[k] = p;
-					}
-					// The reference sorts the projections and walks the cluster boundaries (k + 0.5 - s) * t with one
-					// running k (:1977-1984). The boundaries are non-decreasing in k (t >= 0), so for sorted input the
-					// running k of an element equals the NUMBER of boundaries it exceeds: no sort, no dependent loop.
-					real bound[15];
-#pragma unroll 1
-					for (int k = 0; k < clusters - 1; k++) bound[k] = ((real) k + 0.5 - s) * t;
-					b = 0;
-#pragma unroll 1
-					for (int j = 0; j < n; j++) {
-						const real pj = proj[j];
-						int k = 0;
-#pragma unroll 1
-						for (int c = 0; c < clusters - 1; c++) k += (pj > bound[c]) ? 1 : 0;
-						index[j] = k;
-						b |= (uint64_t) k << (4 * j);
-					}
-					slot = memo_next;
-					memo_next = (memo_next + 1) & 3;
-					memo_n = memo_n < 4 ? memo_n + 1 : 4;
-					memo_key[slot] = a;
-					memo_f[slot] = b;
-					memo_gvalid[slot] = 0;
-					have_proj = true;
+				for (int k = 0; k < n; k++) {
+					index[k] = (int) ((a >> (4 * k)) & 15u);
+					s += index[k];
+					t += index[k] * index[k];
 				}
-				done = (b == a);
-				last = slot;
-			} while (!done && try_two--);
-			uint64_t cur = 0;
 #pragma unroll 1
-			for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
-			if (it == 1) first = cur;
-			else if (first == cur) { A7_STATS_IT(it); break; }
-		}
-		if (last >= 0 && memo_gvalid[last]) {
-			const uint64_t g = memo_g[last];
+				for (int j = 0; j < dim; j++) {
+					real d = 0;
 #pragma unroll 1
-			for (int k = 0; k < n; k++) index[k] = (int) ((g >> (4 * k)) & 15u);
+					for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
+					dir[j] = d;
+					q += d * d;
+				}
+				s /= (real) n;
+				t = t - s * s * (real) n;
+				t = (t == 0 ? 0. : 1 / t);
+				q = sqrt(q);
+				t *= q;
+				if (q != 0)
+#pragma unroll 1
+					for (int j = 0; j < dim; j++) dir[j] /= q;
+#pragma unroll 1
+				for (int k = 0; k < n; k++) {
+					real p = 0;
+#pragma unroll 1
+					for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
+					proj[k] = p;
+				}
+				// The reference sorts the projections and walks the cluster boundaries (k + 0.5 - s) * t with one
+				// running k (:1977-1984). The boundaries are non-decreasing in k (t >= 0), so for sorted input the
+				// running k of an element equals the NUMBER of boundaries it exceeds: no sort, no dependent loop.
+				real bound[15];
+#pragma unroll 1
+				for (int k = 0; k < clusters - 1; k++) bound[k] = ((real) k + 0.5 - s) * t;
+				b = 0;
+#pragma unroll 1
+				for (int j = 0; j < n; j++) {
+					const real pj = proj[j];
+					int k = 0;
+#pragma unroll 1
+					for (int c = 0; c < clusters - 1; c++) k += (pj > bound[c]) ? 1 : 0;
+					b |= (uint64_t) k << (4 * j);
+				}
+				slot = memo_next;
+				memo_next = (memo_next + 1) & 3;
+				memo_n = memo_n < 4 ? memo_n + 1 : 4;
+				memo_key[slot] = a;
+				memo_f[slot] = b;
+				memo_gvalid[slot] = 0;
+				have_proj = true;
+			}
+			cur = b;
+			done = (b == a);
+			last = slot;
+		} while (!done && try_two--);
+		if (it == 1) first = cur;
+		else if (first == cur) { A7_STATS_IT(it); break; }
+		if (memo_gvalid[last]) {
+			cur = memo_g[last];
 		} else {
 			if (!have_proj) { // projection of the memoised refit's INPUT indices
 				const uint64_t a = memo_key[last];
@@ -439,17 +448,36 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 					proj[k] = p;
 				}
 			}
+			A7_STATS_G();
 			lattice_quantise(proj, clusters, n, index);
-			if (last >= 0) {
-				uint64_t g = 0;
+			cur = 0;
 #pragma unroll 1
-				for (int k = 0; k < n; k++) g |= (uint64_t) (index[k] & 15) << (4 * k);
-				memo_g[last] = g;
-				memo_gvalid[last] = 1;
+			for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
+			memo_g[last] = cur;
+			memo_gvalid[last] = 1;
+		}
+		// `cur` is now the state at the top of iteration it + 1; states from the top of iteration 2 on are recorded
+		// (every iteration >= 2 runs the convergence test, so a repeat proves that the test fails forever)
+		if (it >= 2) {
+			int period = 0;
+#pragma unroll 1
+			for (int pd = 1; pd <= kHist && pd <= it - 1; pd++) {
+				const int h = (it + 1 - pd) & (kHist - 1);
+				if (hist[h] == cur && (hist_try[h] == try_two || hist_try[h] < 0)) { period = pd; break; }
+			}
+			if (period) {
+				const int r = (kQuantMaxTry - 1 - it) % period; // iterations still to run, modulo the period
+				cur = hist[(it + 1 - period + r) & (kHist - 1)];
+				A7_STATS_IT(kQuantMaxTry + 1);
+				break;
 			}
 		}
-		if (it == 199) { A7_STATS_IT(200); }
+		hist[(it + 1) & (kHist - 1)] = cur;
+		hist_try[(it + 1) & (kHist - 1)] = try_two;
+		if (it == kQuantMaxTry - 1) { A7_STATS_IT(kQuantMaxTry); }
 	}
+#pragma unroll 1
+	for (int k = 0; k < n; k++) index[k] = (int) ((cur >> (4 * k)) & 15u);
 	s = t = 0;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
