@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "bc7amd_block.cuh"
+#include <stdlib.h>
 
 namespace b200ic {
 
@@ -74,9 +75,14 @@ struct WarpScratch {
 	real perr[64];
 	int top[8];
 	ShakeOut so[kMaxTasks];
-	CubeTask task[kMaxTasks];
-	uint64_t item_key[kItemBatch];
-	uint64_t item_idx[kItemBatch];
+	union {
+		struct { // shake phases
+			CubeTask task[kMaxTasks];
+			uint64_t item_key[kItemBatch];
+			uint64_t item_idx[kItemBatch];
+		};
+		real qs[2][16][32]; // quantise phases: the two lane-strided FP64 work arrays of QuantIO (element k of lane l at [k][l])
+	};
 	uint8_t order[kMaxTasks];
 	uint64_t blk[2];
 	real blk_err;
@@ -88,6 +94,7 @@ struct AmdParams {
 	uint64_t n_blocks;
 	const uint32_t *sp;
 	uint32_t mode_mask;
+	int zsplit_single, zsplit_dual; // experiment knobs: 0 = auto / built-in choice
 };
 
 __device__ __forceinline__ uint64_t pack_idx(const int *idx, int n) {
@@ -131,7 +138,8 @@ __device__ __noinline__ void cube_begin_pass(const Tables &T, CubeTask &t, uint6
 }
 
 // ep_shaker_d for all tasks of the warp (u8 path). On return task[i].err_o / best_idx hold its result.
-__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit, unsigned lane) {
+__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit_in, unsigned lane) {
+	int zsplit = zsplit_in > 0 ? zsplit_in : 1;
 	if ((int) lane < ntasks) {
 		CubeTask &t = ws.task[lane];
 		t.err_o = A7_HUGE;
@@ -145,9 +153,18 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 		int count = 0, sortkey = -1;
 		if ((int) lane < ntasks && !ws.task[lane].done) {
 			const CubeTask &t = ws.task[lane];
-			count = qp_count(t.Mi, (1 << t.clog) - 1) * zsplit;
+			count = qp_count(t.Mi, (1 << t.clog) - 1);
 			sortkey = t.clog * 32 + t.n;
 		}
+		if (zsplit_in <= 0) {
+			// cut every item into z-slices of the endpoint cube so that the rounds of 32 lanes are as full as possible:
+			// cost(z) = rounds(z) * (4 / z) quarter-cubes; ties go to the coarser split (the endpoint fit is per item)
+			int tot1 = count;
+			for (int dlt = 16; dlt > 0; dlt >>= 1) tot1 += __shfl_xor_sync(FULL, tot1, dlt);
+			const int c1 = ((tot1 + 31) >> 5) * 4, c2 = ((2 * tot1 + 31) >> 5) * 2, c4 = (4 * tot1 + 31) >> 5;
+			zsplit = c4 < c2 ? (c4 < c1 ? 4 : 1) : (c2 < c1 ? 2 : 1);
+		}
+		count *= zsplit;
 		int rank = 0;
 		for (int o = 0; o < ntasks; o++) {
 			const int ok = __shfl_sync(FULL, sortkey, o);
@@ -374,8 +391,8 @@ __device__ __noinline__ void window_phase(const Tables &T, WarpScratch &ws, int 
 	}
 }
 
-template <bool U8>
-__global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams p) {
+template <bool U8, int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -407,14 +424,22 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 			const ShakeParams sp = single_index_shake_params(mode);
 			const int nparts = 1 << mi.partition_bits, subsets = mi.subsets;
 			const uint8_t *qorder = subsets > 1 ? quantise_order(subsets, nparts) : nullptr;
+			QuantIO io;
+			io.px = &ws.B.pxc[0][0];
+			io.chan = 0xE4u;
+			io.proj = &ws.qs[0][0][lane];
+			io.dev = &ws.qs[1][0][lane];
+			io.stride = 32;
 			for (int tt = (int) lane; tt < nparts * subsets; tt += 32) {
 				const int t = qorder ? qorder[tt] : tt;
 				const int part = t / subsets, s = t - part * subsets;
-				real sub[kMaxEntries][4];
-				int n, idx[kMaxEntries];
-				gather_subset(ws.B, subsets, part, s, sp.dim, sub, n);
-				ws.serr[part][s] = n ? quantise_subset(sub, n, sp.clusters, idx, sp.dim) : 0;
-				ws.qidx[part][s] = pack_idx(idx, n);
+				uint32_t smask = 0;
+				for (int i = 0; i < 16; i++) smask |= (subset_of(subsets, part, i) == s ? 1u : 0u) << i;
+				int n;
+				io.texels = texels_of_mask(smask, n);
+				uint64_t packed = 0;
+				ws.serr[part][s] = n ? quantise_subset(io, n, sp.clusters, sp.dim, packed) : 0;
+				ws.qidx[part][s] = packed;
 			}
 			__syncwarp();
 			for (int part = (int) lane; part < nparts; part += 32) {
@@ -465,7 +490,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 			if (U8) {
 				// shake_subset (:709-805): ep_shaker_d, ep_shaker_2_d on the quantiser's indices, and where the former
 				// won, ep_shaker_2_d again on its indices
-				if (cube_u8) cube_phase(T, ws, ntasks, 1, lane);
+				if (cube_u8) cube_phase(T, ws, ntasks, p.zsplit_single ? p.zsplit_single : (subsets == 3 ? 1 : 0), lane); // 3 subsets: small n, the per-item endpoint fit outweighs fuller rounds (measured)
 				window_phase(T, ws, ntasks, lane);
 				if (cube_u8) {
 					if ((int) lane < ntasks) {
@@ -527,6 +552,23 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 			int idx[16], ep[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 			int ib = 2, cb = 5;
 			U8Subset S;
+			uint64_t qpacked = 0;
+			if ((int) lane < ntasks) { // quantise (work arrays overlay the task table: finish on all lanes first)
+				const int combo = (int) lane >> 1, which = (int) lane & 1;
+				const int rot = combo / nsel, isel = combo - rot * nsel;
+				const uint32_t c0 = (uint32_t) rotation_channel(rot, 0), c1 = (uint32_t) rotation_channel(rot, 1),
+											 c2 = (uint32_t) rotation_channel(rot, 2), c3 = (uint32_t) rotation_channel(rot, 3);
+				QuantIO io;
+				io.px = &ws.B.pxc[0][0];
+				io.texels = 0xFEDCBA9876543210ull;
+				io.chan = which == 0 ? (c1 | (c2 << 2) | (c3 << 4)) : (c0 | (c0 << 2) | (c0 << 4));
+				io.proj = &ws.qs[0][0][lane];
+				io.dev = &ws.qs[1][0][lane];
+				io.stride = 32;
+				const int qb = which == 0 ? (isel ? mi.index_bits1 : mi.index_bits0) : (isel ? mi.index_bits0 : mi.index_bits1);
+				quantise_subset(io, 16, 1 << qb, 3, qpacked);
+			}
+			__syncwarp();
 			if ((int) lane < ntasks) {
 				const int combo = (int) lane >> 1, which = (int) lane & 1;
 				const int rot = combo / nsel, isel = combo - rot * nsel;
@@ -542,7 +584,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 				}
 				ib = which == 0 ? (isel ? mi.index_bits1 : mi.index_bits0) : (isel ? mi.index_bits0 : mi.index_bits1);
 				cb = which == 0 ? mi.vector_bits / 3 : mi.scalar_bits;
-				quantise_subset(blkv, 16, 1 << ib, idx, 3);
+				unpack_idx(qpacked, idx, 16);
 				if (U8) {
 					make_u8_subset(blkv, 16, 3, S);
 					CubeTask &t = ws.task[lane];
@@ -561,7 +603,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) bc7amd_kernel(const AmdParams 
 			}
 			__syncwarp();
 			if (U8) {
-				cube_phase(T, ws, ntasks, ntasks <= 8 ? 4 : 2, lane);
+				cube_phase(T, ws, ntasks, p.zsplit_dual ? p.zsplit_dual : (ntasks <= 8 ? 4 : 2), lane);
 				if ((int) lane < ntasks) {
 					CubeTask &t = ws.task[lane];
 					t.w_index = t.best_idx;
@@ -660,9 +702,13 @@ cudaError_t init_bc7amd_tables() {
 		e = cudaMemcpyToSymbol(c_qorder, order, sizeof(order));
 		if (e != cudaSuccess) return e;
 	}
-	e = cudaFuncSetAttribute(bc7amd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
+	e = cudaFuncSetAttribute(bc7amd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(bc7amd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
+	e = cudaFuncSetAttribute(bc7amd_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(bc7amd_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(bc7amd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WarpScratch)));
 	if (e != cudaSuccess) return e;
 	g_sp_table_host[dev] = d;
 	return cudaSuccess;
@@ -679,6 +725,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	p.n_blocks = (uint64_t) img.blocks_x * img.blocks_y * img.slices;
 	p.sp = g_sp_table_host[dev];
 	p.mode_mask = (uint32_t) opts.amd_mode_mask & 0xffu;
+	p.zsplit_single = getenv("B200IC_AMD_ZS") ? atoi(getenv("B200IC_AMD_ZS")) : 0;
+	p.zsplit_dual = getenv("B200IC_AMD_ZD") ? atoi(getenv("B200IC_AMD_ZD")) : 0;
 	if (p.n_blocks == 0) return cudaSuccess;
 	const uint64_t grid = (p.n_blocks + kWarps - 1) / kWarps;
 	const size_t smem = kWarps * sizeof(WarpScratch);
@@ -686,8 +734,11 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	const bool u8 = img.format == B200IC_FMT_R8 || img.format == B200IC_FMT_RG8 || img.format == B200IC_FMT_RGB8 ||
 									img.format == B200IC_FMT_RGB8_SRGB || img.format == B200IC_FMT_RGBA8 || img.format == B200IC_FMT_RGBA8_SRGB ||
 									img.format == B200IC_FMT_BLOCKS_RGBA8;
-	if (u8) bc7amd_kernel<true><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
-	else bc7amd_kernel<false><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
+	static const int variant = getenv("B200IC_AMD_VARIANT") ? atoi(getenv("B200IC_AMD_VARIANT")) : 4;
+	if (u8 && variant == 3) bc7amd_kernel<true, 3><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
+	else if (u8 && variant == 2) bc7amd_kernel<true, 2><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
+	else if (u8) bc7amd_kernel<true, 4><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
+	else bc7amd_kernel<false, 4><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 

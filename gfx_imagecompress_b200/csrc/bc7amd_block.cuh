@@ -22,6 +22,27 @@ A7_HD real shake_subset(const Tables &T, const ShakeParams &sp, const real data[
 	return e1;
 }
 
+// Serial-form helper: quantise subset `s` of `partition` (or, subsets == 0, the whole block with component j taken from
+// channel (chan >> 2j) & 3) with plain local work arrays.
+A7_HD real quantise_serial(const BlockInput &B, int subsets, int partition, int subset, uint32_t chan, int dim, int clusters, int *idx, int &n) {
+	real proj[kMaxEntries], dev[kMaxEntries];
+	uint32_t mask = 0;
+	for (int i = 0; i < 16; i++)
+		if (subsets == 0 || subset_of(subsets, partition, i) == subset) mask |= 1u << i;
+	QuantIO io;
+	io.px = &B.pxc[0][0];
+	io.texels = texels_of_mask(mask, n);
+	io.chan = chan;
+	io.proj = proj;
+	io.dev = dev;
+	io.stride = 1;
+	uint64_t packed = 0;
+	const real e = n ? quantise_subset(io, n, clusters, dim, packed) : 0;
+	for (int k = 0; k < n; k++) idx[k] = (int) ((packed >> (4 * k)) & 15u);
+	return e;
+}
+constexpr uint32_t kChanRGBA = 0xE4u; // component j <- channel j
+
 // CompressSingleIndexBlock (:548-890)
 template <bool U8> A7_HDN real compress_single_index(const Tables &T, const BlockInput &B, int mode, uint64_t out[2]) {
 	const ModeInfo mi = mode_info(mode);
@@ -31,10 +52,9 @@ template <bool U8> A7_HDN real compress_single_index(const Tables &T, const Bloc
 	for (int part = 0; part < nparts; part++) {
 		real e = 0;
 		for (int s = 0; s < mi.subsets; s++) {
-			real sub[kMaxEntries][4];
 			int n, idx[kMaxEntries];
-			gather_subset(B, mi.subsets, part, s, sp.dim, sub, n);
-			if (n) e += quantise_subset(sub, n, sp.clusters, idx, sp.dim);
+			const real es = quantise_serial(B, mi.subsets, part, s, kChanRGBA, sp.dim, sp.clusters, idx, n);
+			if (n) e += es;
 		}
 		perr[part] = e;
 	}
@@ -53,7 +73,7 @@ template <bool U8> A7_HDN real compress_single_index(const Tables &T, const Bloc
 			int n;
 			gather_subset(B, mi.subsets, part, s, sp.dim, sub, n);
 			if (!n) continue;
-			quantise_subset(sub, n, sp.clusters, cur.idx[s], sp.dim); // the reference stored these in the first pass
+			quantise_serial(B, mi.subsets, part, s, kChanRGBA, sp.dim, sp.clusters, cur.idx[s], n); // the reference stored these in the first pass
 			for (int k = 0; k < 4; k++) cur.ep[s][0][k] = cur.ep[s][1][k] = 0;
 			if (U8) {
 				U8Subset S;
@@ -92,8 +112,11 @@ template <bool U8> A7_HD void dual_index_combo(const Tables &T, const BlockInput
 	}
 	const int ib[2] = {mi.index_bits0, mi.index_bits1};
 	const int vb = mi.vector_bits / 3, sb = mi.scalar_bits;
-	quantise_subset(cb, 16, 1 << ib[isel], r.idx[0], 3);
-	quantise_subset(ab, 16, 1 << ib[1 ^ isel], r.idx[1], 3);
+	int n16;
+	const uint32_t c0 = (uint32_t) rotation_channel(rotation, 0), c1 = (uint32_t) rotation_channel(rotation, 1),
+								 c2 = (uint32_t) rotation_channel(rotation, 2), c3 = (uint32_t) rotation_channel(rotation, 3);
+	quantise_serial(B, 0, 0, 0, c1 | (c2 << 2) | (c3 << 4), 3, 1 << ib[isel], r.idx[0], n16);
+	quantise_serial(B, 0, 0, 0, c0 | (c0 << 2) | (c0 << 4), 3, 1 << ib[1 ^ isel], r.idx[1], n16);
 	const int bits0[4] = {vb, vb, vb, 6 * vb}, bits1[4] = {sb, sb, sb, 6 * sb};
 	for (int i = 0; i < 2; i++)
 		for (int e = 0; e < 2; e++)

@@ -50,6 +50,7 @@ typedef double real;
 #define A7_STATS_F()
 #define A7_STATS_G()
 #define A7_STATS_REPLAY()
+#define A7_STATS_OVF(v)
 #endif
 
 constexpr int kMaxEntries = 16;
@@ -231,118 +232,211 @@ A7_HDN void dominant_axis(const real cov[4][4], real axis[4], int dim) {
 	else dominant_axis_t<4>(cov, axis);
 }
 
-// quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of n scalars (lattice A_n* decoding)
-A7_HDN void lattice_quantise(const real *v_, int k, int n, int *idx) {
-	real m = v_[0], M = v_[0];
+// ---- quantiser I/O --------------------------------------------------------------------------------------------
+// A quantiser call reads its n points straight from the block (channel-major, so that the 32 lanes of a warp -- each
+// working on another subset of the same block -- hit 16 different bank pairs or broadcast) and keeps its two
+// n-element FP64 work arrays in caller-provided storage: lane-strided shared memory on the GPU (element k at
+// [k * stride]: conflict-free, no local-memory traffic), plain local arrays on the host.
+struct QuantIO {
+	const real *px;   // px[channel * 16 + texel], 0..255
+	uint64_t texels;  // 4 bits per entry: texel of entry k
+	uint32_t chan;    // 2 bits per component: source channel of component j
+	real *proj, *dev; // work arrays
+	int stride;
+};
+A7_HD real quant_point(const QuantIO &io, int k, int j) {
+	return io.px[((io.chan >> (2 * j)) & 3u) * 16u + (uint32_t) ((io.texels >> (4 * k)) & 15u)];
+}
+A7_HD uint64_t texels_of_mask(uint32_t mask16, int &n) { // entries in texel order
+	uint64_t t = 0;
+	n = 0;
+#pragma unroll 1
+	for (int i = 0; i < 16; i++)
+		if (mask16 & (1u << i)) {
+			t |= (uint64_t) i << (4 * n);
+			n++;
+		}
+	return t;
+}
+
+// quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of the n scalars io.proj[] (lattice A_n* decoding).
+// Returns the indices packed 4 bits per entry (values taken & 15 like every consumer does).
+A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
+	const int st = io.stride;
+	real m = io.proj[0], M = m;
 #pragma unroll 1
 	for (int i = 1; i < n; i++) {
-		m = m < v_[i] ? m : v_[i];
-		M = M > v_[i] ? M : v_[i];
+		const real v = io.proj[i * st];
+		m = m < v ? m : v;
+		M = M > v ? M : v;
 	}
-	if (M == m) {
-#pragma unroll 1
-		for (int i = 0; i < n; i++) idx[i] = 0;
-		return;
-	}
+	if (M == m) return 0;
 	const real s = (real) (k - 1) / (M - m);
-	real d[kMaxEntries];
 	real dm = 0, r = 0;
+	uint64_t z4 = 0; // floor values, one nibble each (0 .. k-1)
 #pragma unroll 1
 	for (int i = 0; i < n; i++) {
-		const real v = v_[i] * s;
+		const real v = io.proj[i * st] * s;
 		const real z = floor(v + 0.5 - m * s);
-		idx[i] = (int) z;
-		d[i] = v - z - m * s;
-		dm += d[i];
-		r += d[i] * d[i];
+		z4 |= (uint64_t) ((int) z & 15) << (4 * i);
+		const real d = v - z - m * s;
+		io.dev[i * st] = d;
+		dm += d;
+		r += d * d;
 	}
+	uint32_t inc = 0; // entries moved one level up
 	if ((real) n * r - dm * dm >= (real) (n - 1) / 4 / 2) {
 		dm /= (real) n;
 #pragma unroll 1
-		for (int i = 0; i < n; i++) d[i] -= dm;
-		int ord[kMaxEntries];
-		sort_order(d, ord, n);
+		for (int i = 0; i < n; i++) io.dev[i * st] -= dm;
+		// stable rank of every deviation (what an insertion sort with the comparator `a - b > 0` produces)
+		uint64_t ord = 0;
+#pragma unroll 1
+		for (int i = 0; i < n; i++) {
+			const real ki = io.dev[i * st];
+			int rank = 0;
+#pragma unroll 1
+			for (int j = 0; j < n; j++) {
+				const real kj = io.dev[j * st];
+				rank += ((ki - kj > 0) || (!(kj - ki > 0) && j < i)) ? 1 : 0;
+			}
+			ord |= (uint64_t) i << (4 * rank);
+		}
 		real mm = 0, l = 0;
 		int j = -1;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
-			l += d[ord[i]] - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
+			l += io.dev[(int) ((ord >> (4 * i)) & 15u) * st] - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
 			if (l < mm) { mm = l; j = i; }
 		}
 		j = (j + 1) % n;
 #pragma unroll 1
-		for (int i = j; i < n; i++) idx[ord[i]]++;
+		for (int i = j; i < n; i++) inc |= 1u << (int) ((ord >> (4 * i)) & 15u);
 	}
-	int mi = idx[0];
+	int mi = 99;
 #pragma unroll 1
-	for (int i = 1; i < n; i++) mi = mi < idx[i] ? mi : idx[i];
+	for (int i = 0; i < n; i++) {
+		const int v = (int) ((z4 >> (4 * i)) & 15u) + (int) ((inc >> i) & 1u);
+		mi = mi < v ? mi : v;
+	}
+	uint64_t out = 0;
 #pragma unroll 1
-	for (int i = 0; i < n; i++) idx[i] -= mi;
+	for (int i = 0; i < n; i++) {
+		const int v = (int) ((z4 >> (4 * i)) & 15u) + (int) ((inc >> i) & 1u) - mi;
+		A7_STATS_OVF(v);
+		out |= (uint64_t) (v & 15) << (4 * i);
+	}
+	return out;
 }
 
-// optQuantAnD_d (:1874-2045): PCA line + iterative optimal uniform quantiser. Returns the SSE; index[] out.
-A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *index, int dim) {
-	real cen[kMaxEntries][4], mean[4], cov[4][4];
+// refit (:1923-1956): direction through the index-weighted centred points, projections into io.proj; s, t out
+template <int DIM> A7_HD void quant_refit(const QuantIO &io, const real *mean, int n, uint64_t a, bool want_st, real &s, real &t) {
+	real dir[DIM], q = 0;
+	real ss = 0, tt = 0;
+#pragma unroll
+	for (int j = 0; j < DIM; j++) dir[j] = 0;
 #pragma unroll 1
-	for (int j = 0; j < dim; j++) {
-		real m = 0;
-#pragma unroll 1
-		for (int k = 0; k < n; k++) m += data[k][j];
-		if (n) m /= (real) n;
-		mean[j] = m;
-#pragma unroll 1
-		for (int k = 0; k < n; k++) cen[k][j] = data[k][j] - m;
+	for (int k = 0; k < n; k++) {
+		const int ik = (int) ((a >> (4 * k)) & 15u);
+		ss += ik;
+		tt += ik * ik;
+#pragma unroll
+		for (int j = 0; j < DIM; j++) dir[j] += (quant_point(io, k, j) - mean[j]) * ik;
 	}
-#pragma unroll 1
-	for (int i = 0; i < dim; i++)
-#pragma unroll 1
-		for (int j = 0; j <= i; j++) {
-			real c = 0;
-#pragma unroll 1
-			for (int k = 0; k < n; k++) c += cen[k][i] * cen[k][j];
-			cov[i][j] = c;
-			cov[j][i] = c;
-		}
-	real t = 0;
-#pragma unroll 1
-	for (int j = 0; j < dim; j++) t += cov[j][j];
-	if (t < (1. / 256.) || n == 0) {
-#pragma unroll 1
-		for (int i = 0; i < n; i++) index[i] = 0;
-		return 0;
+#pragma unroll
+	for (int j = 0; j < DIM; j++) q += dir[j] * dir[j];
+	if (want_st) {
+		ss /= (real) n;
+		tt = tt - ss * ss * (real) n;
+		tt = (tt == 0 ? 0. : 1 / tt);
 	}
-	real dir[4] = {0, 0, 0, 0}, proj[kMaxEntries];
-	dominant_axis(cov, dir, dim);
+	q = sqrt(q);
+	if (want_st) tt *= q;
+	if (q != 0)
+#pragma unroll
+		for (int j = 0; j < DIM; j++) dir[j] /= q;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		real p = 0;
+#pragma unroll
+		for (int j = 0; j < DIM; j++) p += (quant_point(io, k, j) - mean[j]) * dir[j];
+		io.proj[k * io.stride] = p;
+	}
+	s = ss;
+	t = tt;
+}
+
+// optQuantAnD_d (:1874-2045): PCA line + iterative optimal uniform quantiser over the n points of `io`.
+// Returns the SSE; index_out = final indices, 4 bits per entry.
+template <int DIM> A7_HD real quantise_points(const QuantIO &io, int n, int clusters, uint64_t &index_out) {
+	index_out = 0;
+	if (n == 0) return 0;
+	const int st = io.stride;
+	real mean[DIM];
+#pragma unroll
+	for (int j = 0; j < DIM; j++) mean[j] = 0;
 #pragma unroll 1
-		for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
-		proj[k] = p;
+	for (int k = 0; k < n; k++)
+#pragma unroll
+		for (int j = 0; j < DIM; j++) mean[j] += quant_point(io, k, j);
+#pragma unroll
+	for (int j = 0; j < DIM; j++) mean[j] /= (real) n;
+	real cov[4][4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) cov[i][j] = 0;
+#pragma unroll 1
+	for (int k = 0; k < n; k++) {
+		real c[DIM];
+#pragma unroll
+		for (int j = 0; j < DIM; j++) c[j] = quant_point(io, k, j) - mean[j];
+#pragma unroll
+		for (int i = 0; i < DIM; i++)
+#pragma unroll
+			for (int j = 0; j <= i; j++) cov[i][j] += c[i] * c[j];
+	}
+	real t = 0;
+#pragma unroll
+	for (int i = 0; i < DIM; i++) {
+		t += cov[i][i];
+#pragma unroll
+		for (int j = 0; j < i; j++) cov[j][i] = cov[i][j];
+	}
+	if (t < (1. / 256.)) return 0;
+	{
+		real dir[4] = {0, 0, 0, 0};
+		dominant_axis(cov, dir, DIM);
+#pragma unroll 1
+		for (int k = 0; k < n; k++) {
+			real p = 0;
+#pragma unroll
+			for (int j = 0; j < DIM; j++) p += (quant_point(io, k, j) - mean[j]) * dir[j];
+			io.proj[k * st] = p;
+		}
 	}
 	// The loop below is the reference's (:1911-2007), including its quirks: the convergence test compares against
 	// the indices of iteration 1 (the `index_[j]=index_[j]` no-op, :1997), so an assignment that oscillates never
 	// "converges" and runs all 200 iterations (0.3 .. 1.4 % of the calls, 100x the cost of the rest).  Both steps of an
 	// iteration are PURE functions of the current index vector -- refit+reassign F(index) and the lattice quantiser
 	// G(projection(index)) -- so
-	//   * the state is carried as one packed 64-bit word `cur` (4 bits per entry) and F / G are memoised on it: a replayed
-	//     step costs a few compares;
+	//   * the state is carried as one packed 64-bit word `cur` (4 bits per entry) and F / G are memoised on it (four
+	//     slots held in registers): a replayed step costs a few compares;
 	//   * an iteration is a pure function of (cur, try_two): once the state after G repeats one of the last 8 states
 	//     with try_two unchanged (or already negative: `try_two--` then never cuts a refit chain again) the remaining
 	//     iterations are periodic and no iteration of the period passed the convergence test, so the final state is
 	//     read from the history instead of being replayed (kHist covers every period seen; longer ones just replay).
-	uint64_t memo_key[4], memo_f[4], memo_g[4];
-	int memo_gvalid[4] = {0, 0, 0, 0}, memo_n = 0, memo_next = 0;
+	uint64_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0, mf0 = 0, mf1 = 0, mf2 = 0, mf3 = 0, mg0 = 0, mg1 = 0, mg2 = 0, mg3 = 0;
+	uint32_t gvalid = 0;
+	int memo_n = 0, memo_next = 0;
 	constexpr int kHist = 8;
 	uint64_t hist[kHist];
 	int hist_try[kHist];
-	uint64_t first = 0, cur = 0;
+	uint64_t first = 0;
 	int try_two = 50;
 	real s;
-	lattice_quantise(proj, clusters, n, index); // iteration 0
 	A7_STATS_G();
-#pragma unroll 1
-	for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
+	uint64_t cur = lattice_quantise(io, clusters, n); // iteration 0
 	int it = 1;
 #pragma unroll 1
 	for (; it < kQuantMaxTry; it++) {
@@ -352,68 +446,36 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 		do {
 			const uint64_t a = cur;
 			int slot = -1;
-#pragma unroll 1
-			for (int m = 0; m < memo_n; m++)
-				if (memo_key[m] == a) slot = m;
+			if (memo_n > 0 && mk0 == a) slot = 0;
+			if (memo_n > 1 && mk1 == a) slot = 1;
+			if (memo_n > 2 && mk2 == a) slot = 2;
+			if (memo_n > 3 && mk3 == a) slot = 3;
 			uint64_t b;
 			if (slot >= 0) {
 				A7_STATS_REPLAY();
-				b = memo_f[slot];
+				b = slot == 0 ? mf0 : (slot == 1 ? mf1 : (slot == 2 ? mf2 : mf3));
 				have_proj = false;
 			} else {
 				A7_STATS_F();
-				real q = 0;
-				s = t = 0;
-#pragma unroll 1
-				for (int k = 0; k < n; k++) {
-					index[k] = (int) ((a >> (4 * k)) & 15u);
-					s += index[k];
-					t += index[k] * index[k];
-				}
-#pragma unroll 1
-				for (int j = 0; j < dim; j++) {
-					real d = 0;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
-					dir[j] = d;
-					q += d * d;
-				}
-				s /= (real) n;
-				t = t - s * s * (real) n;
-				t = (t == 0 ? 0. : 1 / t);
-				q = sqrt(q);
-				t *= q;
-				if (q != 0)
-#pragma unroll 1
-					for (int j = 0; j < dim; j++) dir[j] /= q;
-#pragma unroll 1
-				for (int k = 0; k < n; k++) {
-					real p = 0;
-#pragma unroll 1
-					for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
-					proj[k] = p;
-				}
+				quant_refit<DIM>(io, mean, n, a, true, s, t);
 				// The reference sorts the projections and walks the cluster boundaries (k + 0.5 - s) * t with one
 				// running k (:1977-1984). The boundaries are non-decreasing in k (t >= 0), so for sorted input the
 				// running k of an element equals the NUMBER of boundaries it exceeds: no sort, no dependent loop.
-				real bound[15];
-#pragma unroll 1
-				for (int k = 0; k < clusters - 1; k++) bound[k] = ((real) k + 0.5 - s) * t;
 				b = 0;
 #pragma unroll 1
-				for (int j = 0; j < n; j++) {
-					const real pj = proj[j];
-					int k = 0;
+				for (int c = 0; c < clusters - 1; c++) {
+					const real bound = ((real) c + 0.5 - s) * t;
 #pragma unroll 1
-					for (int c = 0; c < clusters - 1; c++) k += (pj > bound[c]) ? 1 : 0;
-					b |= (uint64_t) k << (4 * j);
+					for (int j = 0; j < n; j++) b += (uint64_t) (io.proj[j * st] > bound ? 1 : 0) << (4 * j);
 				}
 				slot = memo_next;
 				memo_next = (memo_next + 1) & 3;
 				memo_n = memo_n < 4 ? memo_n + 1 : 4;
-				memo_key[slot] = a;
-				memo_f[slot] = b;
-				memo_gvalid[slot] = 0;
+				if (slot == 0) { mk0 = a; mf0 = b; }
+				else if (slot == 1) { mk1 = a; mf1 = b; }
+				else if (slot == 2) { mk2 = a; mf2 = b; }
+				else { mk3 = a; mf3 = b; }
+				gvalid &= ~(1u << slot);
 				have_proj = true;
 			}
 			cur = b;
@@ -422,39 +484,21 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 		} while (!done && try_two--);
 		if (it == 1) first = cur;
 		else if (first == cur) { A7_STATS_IT(it); break; }
-		if (memo_gvalid[last]) {
-			cur = memo_g[last];
+		if ((gvalid >> last) & 1u) {
+			cur = last == 0 ? mg0 : (last == 1 ? mg1 : (last == 2 ? mg2 : mg3));
 		} else {
 			if (!have_proj) { // projection of the memoised refit's INPUT indices
-				const uint64_t a = memo_key[last];
-				real q = 0;
-#pragma unroll 1
-				for (int j = 0; j < dim; j++) {
-					real d = 0;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) d += cen[k][j] * (int) ((a >> (4 * k)) & 15u);
-					dir[j] = d;
-					q += d * d;
-				}
-				q = sqrt(q);
-				if (q != 0)
-#pragma unroll 1
-					for (int j = 0; j < dim; j++) dir[j] /= q;
-#pragma unroll 1
-				for (int k = 0; k < n; k++) {
-					real p = 0;
-#pragma unroll 1
-					for (int i = 0; i < dim; i++) p += cen[k][i] * dir[i];
-					proj[k] = p;
-				}
+				const uint64_t a = last == 0 ? mk0 : (last == 1 ? mk1 : (last == 2 ? mk2 : mk3));
+				real s2, t2;
+				quant_refit<DIM>(io, mean, n, a, false, s2, t2);
 			}
 			A7_STATS_G();
-			lattice_quantise(proj, clusters, n, index);
-			cur = 0;
-#pragma unroll 1
-			for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
-			memo_g[last] = cur;
-			memo_gvalid[last] = 1;
+			cur = lattice_quantise(io, clusters, n);
+			if (last == 0) mg0 = cur;
+			else if (last == 1) mg1 = cur;
+			else if (last == 2) mg2 = cur;
+			else mg3 = cur;
+			gvalid |= 1u << last;
 		}
 		// `cur` is now the state at the top of iteration it + 1; states from the top of iteration 2 on are recorded
 		// (every iteration >= 2 runs the convergence test, so a repeat proves that the test fails forever)
@@ -476,33 +520,38 @@ A7_HDN real quantise_subset(const real data[][4], int n, int clusters, int *inde
 		hist_try[(it + 1) & (kHist - 1)] = try_two;
 		if (it == kQuantMaxTry - 1) { A7_STATS_IT(kQuantMaxTry); }
 	}
-#pragma unroll 1
-	for (int k = 0; k < n; k++) index[k] = (int) ((cur >> (4 * k)) & 15u);
+	// final reconstruction error (:2010-2043)
+	real dir[DIM];
 	s = t = 0;
+#pragma unroll
+	for (int j = 0; j < DIM; j++) dir[j] = 0;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
-		s += index[k];
-		t += index[k] * index[k];
-	}
-#pragma unroll 1
-	for (int j = 0; j < dim; j++) {
-		real d = 0;
-#pragma unroll 1
-		for (int k = 0; k < n; k++) d += cen[k][j] * index[k];
-		dir[j] = d;
+		const int ik = (int) ((cur >> (4 * k)) & 15u);
+		s += ik;
+		t += ik * ik;
+#pragma unroll
+		for (int j = 0; j < DIM; j++) dir[j] += (quant_point(io, k, j) - mean[j]) * ik;
 	}
 	s /= (real) n;
 	t = t - s * s * (real) n;
 	t = (t == 0 ? 0. : 1 / t);
 	real err = 0;
 #pragma unroll 1
-	for (int i = 0; i < n; i++)
-#pragma unroll 1
-		for (int j = 0; j < dim; j++) {
-			const real o = mean[j] + dir[j] * t * ((real) index[i] - s);
-			err += (data[i][j] - o) * (data[i][j] - o);
+	for (int i = 0; i < n; i++) {
+		const int ii = (int) ((cur >> (4 * i)) & 15u);
+#pragma unroll
+		for (int j = 0; j < DIM; j++) {
+			const real v = quant_point(io, i, j);
+			const real o = mean[j] + dir[j] * t * ((real) ii - s);
+			err += (v - o) * (v - o);
 		}
+	}
+	index_out = cur;
 	return err;
+}
+A7_HDN real quantise_subset(const QuantIO &io, int n, int clusters, int dim, uint64_t &index_out) {
+	return dim == 3 ? quantise_points<3>(io, n, clusters, index_out) : quantise_points<4>(io, n, clusters, index_out);
 }
 
 // ep_find_floor (:351-367)
@@ -1102,6 +1151,7 @@ A7_HDN void pack_dual_index(int mode, int index_selection, int rotation, int ep[
 // ---- block level (serial orchestration; the CUDA kernel spreads the same tasks over lanes) ---------------
 struct BlockInput {
 	real px[16][4]; // 0..255
+	real pxc[4][16]; // the same, channel-major (quantiser input, see QuantIO)
 	uint32_t mode_mask; // after the filter of :1340-1380
 };
 
@@ -1118,6 +1168,7 @@ A7_HDN void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInp
 		for (int j = 0; j < 4; j++) {
 			const real v = (real) (in[i * 4 + j] * 255.0f);
 			B.px[i][j] = v;
+			B.pxc[j][i] = v;
 			mn[j] = v < mn[j] ? v : mn[j];
 			mx[j] = v > mx[j] ? v : mx[j];
 		}
