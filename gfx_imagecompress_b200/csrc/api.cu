@@ -148,6 +148,8 @@ static int ensure_device() {
 	return 0;
 }
 
+void count_launches(int extra) { g_launches.fetch_add((uint64_t) extra, std::memory_order_relaxed); }
+
 static int dispatch(int codec, const SrcImage &img, const b200ic_opts &o, void *d_dst, cudaStream_t stream) {
 	cudaError_t e;
 	switch (codec) {

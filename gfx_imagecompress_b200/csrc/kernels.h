@@ -10,6 +10,7 @@ cudaError_t launch_bc1(const SrcImage &img, const b200ic_opts &opts, void *dst, 
 cudaError_t launch_bc7rg(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
 cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
 cudaError_t launch_bc6h(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
+void count_launches(int extra); // launchers issuing more than one kernel per encode report the extra ones
 cudaError_t init_bc7rg_tables();
 cudaError_t init_bc7amd_tables();
 cudaError_t init_bc6h_tables();
