@@ -41,6 +41,28 @@ def _peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def _counters(cname):
+    """Per-block counters of the codec's kernel(s) from one `ncu --set full` capture (tools/ncu_counters.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_counters.json")) as f:
+            return json.load(f).get(cname)
+    except Exception:
+        return None
+
+
+def _alu(cname, blocks_per_s, sm_mhz):
+    """Issue side of the roofline: executed thread-instructions (lane-ops) per second against 148 SMs x 128 lanes x clock.
+    The kernels are built --fmad=false, so one lane-op is at most one flop."""
+    c = _counters(cname)
+    if not c:
+        return None
+    peak = 148 * 128 * float(sm_mhz or 1965.0) * 1e6
+    ach = c["thread_inst_per_block"] * blocks_per_s
+    return {"achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T lane-ops/s", "frac": ach / peak,
+            "thread_inst_per_block": c["thread_inst_per_block"], "warp_inst_per_block": c["warp_inst_per_block"],
+            "lanes_per_inst": c["thread_inst_per_block"] / max(c["warp_inst_per_block"], 1.0), "source": "profiles/" + c["report"]}
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -371,17 +393,25 @@ def main():
         alg_bytes = size * size * wl["bpt"] + nblocks * bb
         k_ms = sum(per_launch_ms) / len(per_launch_ms)
         achieved = alg_bytes / (k_ms / 1e3) / 1e9
+        ctr = _counters(cname)
+        clk = clocks.summary()
         out = {"metric": metric, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f64" if codec == 7 else "f32", "data": "synthetic", "config": cfg,
                "e2e": {"value": e2e_v, "unit": "Mpix/s", "h2d_bytes_per_step": int(host_np.nbytes), "d2h_bytes_per_step": int(nblocks * bb),
                        "matches_device_path": same},
-               "gpu_launches": int(launches), "clocks": clocks.summary(),
+               "gpu_launches": int(launches), "clocks": clk,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
+                            "frac": achieved / peaks["hbm_gbs"],
+                            "traffic": (ctr["dram_bytes_per_block"] * nblocks) if ctr else None, "peak_source": how,
                             "kernel": f"{cname}_kernel", "algorithmic_bytes_per_launch": alg_bytes,
-                            "note": "per-block search is ALU bound (SURVEY.md 8d); see DESIGN.md for the ALU-side accounting"},
+                            "launches_per_step": int(launches) // max(args.steps, 1),
+                            "note": "achieved / traffic / algorithmic bytes are per step (= per image: every launch of the step "
+                                    "together; AMD BC7 is one launch per mode); traffic = ncu dram bytes per block of "
+                                    + (f"profiles/{ctr['report']} ({ctr['blocks']} blocks)" if ctr else "n/a") +
+                                    " x the blocks of this workload. The per-block search is ALU bound (SURVEY.md 8d): see `alu`"},
                "blocks_per_s": world * nblocks * args.steps / (total_ms_max / 1e3)}
+        out["alu"] = _alu(cname, out["blocks_per_s"] / world, clk.get("sm_mhz"))
         if not args.no_cpu and world == 1:
             _, info = cpu_reference_sample(codec, size, 3, args.cpu_budget, 1)
             out["cpu_baseline"] = info

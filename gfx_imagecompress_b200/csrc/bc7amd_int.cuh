@@ -50,54 +50,70 @@ template <int CLOG> A7_HD void ramp_bytes(int e1, int e2, uint64_t out[(1 << CLO
 	}
 }
 
-struct ClusterStats {
-	int cnt[16];
-	int sum[16][4];
+// ---- per-cluster statistics in registers --------------------------------------------------------------------------
+// One 64-bit word per cluster: count in bits 0..7, channel sums (<= 16 * 255) in 14-bit fields at bits 8 + 14 j.  The
+// words are indexed statically (loops over the cluster are unrolled), so they live in registers: no local-memory
+// traffic in the innermost shaker loops.
+template <int CLOG> struct ClusterAcc {
+	uint64_t a[1 << CLOG];
 };
-// per-cluster counts and channel sums of packed texels d[] under index assignment cidx[]
-A7_HDN void cluster_stats(const uint32_t *d, int n, const int *cidx, int Mi_, int dim, ClusterStats &cs) {
-#pragma unroll 1
-	for (int c = 0; c <= Mi_; c++) {
-		cs.cnt[c] = 0;
-#pragma unroll 1
-		for (int j = 0; j < 4; j++) cs.sum[c][j] = 0;
-	}
-#pragma unroll 1
-	for (int i = 0; i < n; i++) {
-		const int c = cidx[i];
-		cs.cnt[c]++;
-#pragma unroll 1
-		for (int j = 0; j < dim; j++) cs.sum[c][j] += (int) ((d[i] >> (8 * j)) & 255u);
-	}
+A7_HD uint64_t acc_entry(uint32_t texel) { // one texel as an accumulator increment
+	const uint32_t lo = 1u | ((texel & 255u) << 8) | (((texel >> 8) & 255u) << 22);
+	const uint32_t hi = (((texel >> 16) & 255u) << 4) | ((texel >> 24) << 18);
+	return (uint64_t) lo | ((uint64_t) hi << 32);
 }
-// fit_endpoints on exact-integer data (same FP64 operations as the reference; sums of integers are exact)
-A7_HDN void fit_endpoints_u8(const ClusterStats &cs, const int *cidx, int n, int Mi_, int dim, real epa[2][4]) {
-	real cc[16][4];
-#pragma unroll 1
-	for (int c = 0; c <= Mi_; c++)
-		if (cs.cnt[c])
-#pragma unroll 1
-			for (int j = 0; j < dim; j++) cc[c][j] = floor((real) cs.sum[c][j] / (real) cs.cnt[c] + 0.5);
-	real im00 = 0, im01 = 0, im11 = 0, rp[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+A7_HD int acc_count(uint64_t a) { return (int) (a & 255u); }
+A7_HD int acc_sum(uint64_t a, int j) { return (int) ((a >> (8 + 14 * j)) & 0x3fffu); }
+template <int CLOG> A7_HD void cluster_acc(const uint32_t *d, int n, uint64_t collapsed, int q, int p, ClusterAcc<CLOG> &cs) {
+	constexpr int C = 1 << CLOG;
+#pragma unroll
+	for (int c = 0; c < C; c++) cs.a[c] = 0;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
-		const int a = Mi_ - cidx[k], b = cidx[k];
-		im00 += a * a;
-		im01 += b * a;
-		im11 += b * b;
-#pragma unroll 1
-		for (int j = 0; j < dim; j++) {
-			rp[0][j] += (real) a * cc[b][j];
-			rp[1][j] += (real) b * cc[b][j];
+		const int ck = (int) ((collapsed >> (4 * k)) & 15u) * q + p;
+		const uint64_t e = acc_entry(d[k]);
+#pragma unroll
+		for (int c = 0; c < C; c++) cs.a[c] += (ck == c) ? e : 0ull;
+	}
+}
+// floor(x / d) for 1 <= d <= 16, 0 <= x < 32768: (x * (2^20 / d + 1)) >> 20
+static B7T_QUAL uint32_t kInv20[17] = {0,     1048577, 524289, 349526, 262145, 209716, 174763, 149797, 131073,
+																116509, 104858,  95326,  87382,  80660,  74899,  69906,  65537};
+// Least-squares endpoints (:1167-1199 / :852-884) from the cluster statistics.  The cluster means
+// floor(sum / cnt + 0.5) are exact small integers (the rounding cannot flip: the exact value is a multiple of
+// 1 / (2 cnt) >= 1/32 away from any other integer, and m - 0.5 is exactly representable), and every sum the reference
+// forms over the texels is a sum of integers, so it is done per cluster in INT32; only the 2x2 solve keeps the
+// reference's FP64 operations.
+template <int CLOG> A7_HD void fit_endpoints_acc(const ClusterAcc<CLOG> &cs, int dim, real epa[2][4]) {
+	constexpr int C = 1 << CLOG, Mi_ = C - 1;
+	int im00 = 0, im01 = 0, im11 = 0, rp0[4] = {0, 0, 0, 0}, rp1[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int c = 0; c < C; c++) {
+		const int cnt = acc_count(cs.a[c]);
+		if (cnt) {
+			const int a = Mi_ - c, b = c;
+			im00 += cnt * a * a;
+			im01 += cnt * a * b;
+			im11 += cnt * b * b;
+			const uint32_t inv = kInv20[cnt];
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				if (j < dim) {
+					const int cc = (int) (((uint64_t) (uint32_t) (2 * acc_sum(cs.a[c], j) + cnt) * inv) >> 21); // floor(x / cnt) / 2 = floor(x / (2 cnt)); 64-bit product: up to 2^33
+					rp0[j] += cnt * a * cc;
+					rp1[j] += cnt * b * cc;
+				}
 		}
 	}
-	const real dd = im00 * im11 - im01 * im01;
-	const real i00 = im11 / dd, i11 = im00 / dd, i01 = -im01 / dd;
-#pragma unroll 1
-	for (int j = 0; j < dim; j++) {
-		epa[0][j] = (i00 * rp[0][j] + i01 * rp[1][j]) * (real) Mi_;
-		epa[1][j] = (i01 * rp[0][j] + i11 * rp[1][j]) * (real) Mi_;
-	}
+	const real d00 = (real) im00, d01 = (real) im01, d11 = (real) im11;
+	const real dd = d00 * d11 - d01 * d01;
+	const real i00 = d11 / dd, i11 = d00 / dd, i01 = -d01 / dd;
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+		if (j < dim) {
+			epa[0][j] = (i00 * (real) rp0[j] + i01 * (real) rp1[j]) * (real) Mi_;
+			epa[1][j] = (i01 * (real) rp0[j] + i11 * (real) rp1[j]) * (real) Mi_;
+		}
 }
 
 struct U8Subset {
@@ -221,6 +237,128 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 		}
 }
 
+// The same search as cube_search_u8 with an exact branch-and-bound.  For a corner (x, y, z) of a lattice the error is
+// sum_i min_c [ r(c;x) + g(c;y) + b(c;z) ] >= sum_i min_c r + sum_i min_c g + sum_i min_c b = LB0[x] + LB1[y] + LB2[z]:
+// twelve per-channel minima per lattice bound all 64 corners.  A corner whose bound is strictly above the best error
+// found so far (over all lattices of the item) can neither win nor tie, so it is skipped; the survivors are evaluated
+// exactly as before and the result -- min over corners of err << 8 | lattice << 6 | gray position -- is identical.
+// The corner with the smallest bound goes first; the survivors of a lane are popped from a 64-bit mask, so the lanes
+// of a warp stay in the same code while working on different corners.
+#ifndef A7_STATS_CORNERS
+#define A7_STATS_CORNERS(evaluated, total)
+#endif
+template <int CLOG>
+A7_HD void cube_corner_u8(const uint32_t *d, int n, const uint64_t tab[3][4], int x, int y, int z, int lattice, uint32_t &best_key, uint64_t &best_idx) {
+	constexpr int C = 1 << CLOG;
+	uint32_t pal[C];
+	const uint64_t t0 = tab[0][x], t1 = tab[1][y], t2 = tab[2][z];
+#pragma unroll
+	for (int c = 0; c < C; c++) pal[c] = byte_of(t0, c) | (byte_of(t1, c) << 8) | (byte_of(t2, c) << 16);
+	uint32_t err = 0;
+	uint64_t idx = 0;
+#pragma unroll 1
+	for (int i = 0; i < n; i++) {
+		const uint32_t di = d[i];
+		uint32_t m = 0xffffffffu;
+#pragma unroll
+		for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], di) << 4) | (uint32_t) c);
+		err += m >> 4;
+		idx |= (uint64_t) (m & 15u) << (4 * i);
+	}
+	const uint32_t key = (err << 8) | ((uint32_t) lattice << 6) | (uint32_t) gray_position(x | (y << 2) | (z << 4));
+	if (key < best_key) { best_key = key; best_idx = idx; }
+}
+template <int CLOG>
+A7_HD void cube_search_pruned_u8(const uint32_t *d, int n, const int *bits, const real epa[2][4], int use_par, int bcc, int z0, int z1,
+																 uint32_t &best_key, uint64_t &best_idx) {
+	constexpr int C = 1 << CLOG;
+	int fl[2][3][2];
+#pragma unroll 1
+	for (int e = 0; e < 2; e++)
+#pragma unroll 1
+		for (int k = 0; k < 3; k++)
+#pragma unroll 1
+			for (int par = 0; par <= use_par; par++) fl[e][k][par] = endpoint_floor(epa[e][k], bits[k], use_par, par);
+	int lattice = 0;
+#pragma unroll 1
+	for (int odd = 0; odd <= use_par; odd++)
+#pragma unroll 1
+		for (int flip = 0; flip <= bcc; flip++, lattice++) {
+			uint64_t tab[3][4]; // [channel][ei0 + 2*ei1] -> C ramp bytes
+			uint32_t lb[3][4];  // [channel][combo] -> sum over the texels of the smallest squared distance to the ramp
+#pragma unroll 1
+			for (int k = 0; k < 3; k++) {
+				int ep[2][2];
+#pragma unroll 1
+				for (int e = 0; e < 2; e++) {
+					const int f = fl[e][k][(odd ^ (flip & e)) & 1];
+					const int top = (1 << bits[k]) - 1;
+					ep[e][0] = expand_bits(bits[k], f);
+					ep[e][1] = expand_bits(bits[k], f + ((top - f < (1 << use_par) ? top - f : (1 << use_par)) & ~use_par));
+				}
+#pragma unroll 1
+				for (int x = 0; x < 4; x++) {
+					ramp_bytes<CLOG>(ep[0][x & 1], ep[1][x >> 1], &tab[k][x]);
+					const uint64_t rv = tab[k][x];
+					uint32_t sum = 0;
+#pragma unroll 1
+					for (int i = 0; i < n; i++) {
+						const int v = (int) ((d[i] >> (8 * k)) & 255u);
+						int m = 255;
+#pragma unroll
+						for (int c = 0; c < C; c++) {
+							int a = (int) byte_of(rv, c) - v;
+							a = a < 0 ? -a : a;
+							m = a < m ? a : m;
+						}
+						sum += (uint32_t) (m * m);
+					}
+					lb[k][x] = sum;
+				}
+			}
+			// seed: the corner with the smallest bound (first such in x, y, z order)
+			int sx = 0, sy = 0, sz = z0;
+#pragma unroll 1
+			for (int x = 1; x < 4; x++) {
+				if (lb[0][x] < lb[0][sx]) sx = x;
+				if (lb[1][x] < lb[1][sy]) sy = x;
+			}
+#pragma unroll 1
+			for (int z = z0 + 1; z < z1; z++)
+				if (lb[2][z] < lb[2][sz]) sz = z;
+			int evaluated = 0;
+			if (lb[0][sx] + lb[1][sy] + lb[2][sz] <= (best_key >> 8)) {
+				cube_corner_u8<CLOG>(d, n, tab, sx, sy, sz, lattice, best_key, best_idx);
+				evaluated++;
+			}
+			uint64_t mask = 0;
+#pragma unroll 1
+			for (int z = z0; z < z1; z++)
+#pragma unroll 1
+				for (int y = 0; y < 4; y++) {
+					const uint32_t t = lb[2][z] + lb[1][y];
+#pragma unroll
+					for (int x = 0; x < 4; x++) mask |= (uint64_t) (t + lb[0][x] <= (best_key >> 8) ? 1 : 0) << (x | (y << 2) | (z << 4));
+				}
+			mask &= ~(1ull << (sx | (sy << 2) | (sz << 4)));
+#pragma unroll 1
+			while (mask) {
+#if defined(__CUDA_ARCH__)
+				const int cnr = __ffsll((long long) mask) - 1;
+#else
+				const int cnr = __builtin_ctzll(mask);
+#endif
+				mask &= mask - 1;
+				const int x = cnr & 3, y = (cnr >> 2) & 3, z = cnr >> 4;
+				if (lb[0][x] + lb[1][y] + lb[2][z] <= (best_key >> 8)) {
+					cube_corner_u8<CLOG>(d, n, tab, x, y, z, lattice, best_key, best_idx);
+					evaluated++;
+				}
+			}
+			A7_STATS_CORNERS(evaluated, 16 * (z1 - z0));
+		}
+}
+
 // ---- (q, p) re-indexings of a collapsed index set (the double loop of :1144-1146 / :835-836), as an ordered list
 A7_HD int qp_count(int Mi, int Mi_) {
 	int c = 0;
@@ -241,14 +379,10 @@ A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
 template <int CLOG>
 A7_HDN void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, const int *bits, int type, int z0, int z1, uint32_t &key,
 												uint64_t &idx) {
-	constexpr int Mi_ = (1 << CLOG) - 1;
-	int cidx[kMaxEntries];
-#pragma unroll 1
-	for (int k = 0; k < n; k++) cidx[k] = (int) ((collapsed >> (4 * k)) & 15u) * q + p;
-	ClusterStats cs;
-	cluster_stats(d, n, cidx, Mi_, 3, cs);
+	ClusterAcc<CLOG> cs;
+	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
 	real epa[2][4];
-	fit_endpoints_u8(cs, cidx, n, Mi_, 3, epa);
+	fit_endpoints_acc<CLOG>(cs, 3, epa);
 	key = 0xffffffffu;
 	idx = 0;
 	cube_search_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
@@ -284,13 +418,13 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 		for (int q = 1; q * Mi <= Mi_; q++)
 #pragma unroll 1
 			for (int p = 0; p <= Mi_ - q * Mi; p++) {
-				int cidx[kMaxEntries];
+				uint64_t collapsed = 0;
 #pragma unroll 1
-				for (int k = 0; k < n; k++) cidx[k] = index[k] * q + p;
-				ClusterStats cs;
-				cluster_stats(S.d, n, cidx, Mi_, 3, cs);
+				for (int k = 0; k < n; k++) collapsed |= (uint64_t) (index[k] & 15) << (4 * k);
+				ClusterAcc<CLOG> cs;
+				cluster_acc<CLOG>(S.d, n, collapsed, q, p, cs);
 				real epa[2][4];
-				fit_endpoints_u8(cs, cidx, n, Mi_, 3, epa);
+				fit_endpoints_acc<CLOG>(cs, 3, epa);
 				uint32_t key = 0xffffffffu;
 				uint64_t idx_1 = 0;
 				cube_search_u8<CLOG>(S.d, n, bits, epa, use_par, bcc, 0, 4, key, idx_1);
@@ -340,25 +474,30 @@ A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int
 	const int type = bits_total % (2 * dim);
 	const int use_par = type != 0;
 	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
-	int cidx[kMaxEntries];
 	int sq_total[4] = {0, 0, 0, 0}; // sum of squares of the data per channel
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
-		cidx[k] = (int) ((collapsed >> (4 * k)) & 15u) * q + p;
-#pragma unroll 1
-		for (int j = 0; j < dim; j++) {
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
 			const int b = (int) ((d[k] >> (8 * j)) & 255u);
 			sq_total[j] += b * b;
 		}
 	}
-	ClusterStats cs;
-	cluster_stats(d, n, cidx, Mi_, dim, cs);
+	ClusterAcc<CLOG> cs;
+	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
 	real epa[2][4];
-	fit_endpoints_u8(cs, cidx, n, Mi_, dim, epa);
+	fit_endpoints_acc<CLOG>(cs, dim, epa);
 	int ed[2][2][4], ep2[2][2][2][4];
 	const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
 #pragma unroll 1
-	for (int j = 0; j < dim; j++)
+	for (int j = 0; j < dim; j++) {
+		int cnt[C], sum2[C]; // this channel's cluster counts and doubled sums (static indices: registers)
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+			cnt[c] = acc_count(cs.a[c]);
+			sum2[c] = 2 * acc_sum(cs.a[c], j);
+		}
+		const int sqj = j == 0 ? sq_total[0] : (j == 1 ? sq_total[1] : (j == 2 ? sq_total[2] : sq_total[3]));
 #pragma unroll 1
 		for (int pp0 = 0; pp0 < rr; pp0++)
 #pragma unroll 1
@@ -379,11 +518,11 @@ A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int
 						uint64_t rv[W];
 						ramp_bytes<CLOG>(e1, expand_bits(mb, p2), rv);
 						// sum_m (rv[cidx[m]] - d[m])^2 == sum d^2 + sum_c rv_c * (cnt_c * rv_c - 2 * S1_c)
-						int t = sq_total[j];
+						int t = sqj;
 #pragma unroll
 						for (int c = 0; c < C; c++) {
 							const int r = (int) byte_of(rv[c >> 3], c & 7);
-							t += r * (cs.cnt[c] * r - 2 * cs.sum[c][j]);
+							t += r * (cnt[c] * r - sum2[c]);
 						}
 						if (t < best) { best = t; b1 = p1; b2 = p2; }
 					}
@@ -392,6 +531,7 @@ A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int
 				ep2[pp0][pp1][0][j] = b1;
 				ep2[pp0][pp1][1][j] = b2;
 			}
+	}
 	int64_t err_1 = INT64_MAX;
 	int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll 1

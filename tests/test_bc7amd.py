@@ -29,26 +29,28 @@ def _check(name, got, want, px, min_same=0.98):
     return dp, same
 
 
-def test_core_hostbuild_matches_reference_blocks(ref):
+@pytest.mark.parametrize("u8_path", [False, True], ids=["fp64_shakers", "int_shakers"])
+def test_core_hostbuild_matches_reference_blocks(ref, u8_path):
     import hostbuild
     L = hostbuild.load()
     imgs = [synth.rgba8_gradnoise(32, 16, 3, "lefthalf"), synth.rgba8_gradnoise(16, 16, 4, "opaque"),
             synth.pattern("RGBA", 16, 16)[0], synth.pattern("RGB_Punchthrough", 16, 16)[0]]
     for k, img in enumerate(imgs):
         fb = cases.to_blocks_f32(img)
-        got, _ = hostbuild.bc7amd_blocks(L, fb)
+        got, _ = hostbuild.bc7amd_blocks(L, fb, u8_path=u8_path)
         want = np.stack([_ref_block(ref, b) for b in fb])
         assert np.array_equal(got, want), f"image {k}: {(got != want).any(axis=1).sum()} blocks differ"
 
 
+@pytest.mark.parametrize("u8_path", [False, True], ids=["fp64_shakers", "int_shakers"])
 @pytest.mark.parametrize("mode", range(8))
-def test_core_hostbuild_single_modes(ref, mode):
+def test_core_hostbuild_single_modes(ref, mode, u8_path):
     """Each mode alone through ModeMask (the reference's own switch, src/amd_bc7_body.hpp:103-106)."""
     import hostbuild
     L = hostbuild.load()
     img = synth.rgba8_gradnoise(16, 8, 5, "ramp" if mode >= 4 else "opaque")
     fb = cases.to_blocks_f32(img)
-    got, _ = hostbuild.bc7amd_blocks(L, fb, 1 << mode)
+    got, _ = hostbuild.bc7amd_blocks(L, fb, 1 << mode, u8_path=u8_path)
     want = np.stack([_ref_block(ref, b, 1 << mode) for b in fb])
     assert np.array_equal(got, want)
 

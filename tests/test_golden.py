@@ -67,7 +67,7 @@ def test_cpu_restatements_reproduce_golden(restated, path):
         if g["codec"] == BC1:
             got = hostbuild.bc1_blocks(L, fb, o.get("bc1_alpha_threshold", 128) / 255.0, o.get("amd_refinement_steps", 1))
         elif g["codec"] == BC7:
-            got, _ = hostbuild.bc7amd_blocks(L, fb, o.get("amd_mode_mask", 0xFF))
+            got, _ = hostbuild.bc7amd_blocks(L, fb, o.get("amd_mode_mask", 0xFF), u8_path=px.dtype == np.uint8)
         elif g["codec"] == BC6H:
             got = hostbuild.bc6h_blocks(L, fb)
         else:

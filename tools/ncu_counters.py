@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
-"""Reads `ncu --set full` reports (gpurun_out/*.ncu-rep, read here with `ncu -i`, no GPU needed) and writes
+"""Reads ncu metric captures (`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,
+smsp__thread_inst_executed.sum,gpu__time_duration.sum --csv --log-file X tools/ncu_capture.py codec size`) and writes
 profiles/ncu_counters.json: per codec, the per-encode sums over all launches of the capture (AMD BC7 = one launch per
 mode) of DRAM bytes, executed warp / thread instructions and kernel time, plus the block count of the captured image.
 bench.py scales these per-block figures to its workload for `roofline.traffic` and the `alu` object.
 
-usage: ncu_counters.py codec=report.ncu-rep:blocks [...]"""
+usage: ncu_counters.py codec=capture.csv:blocks [...]"""
 import csv
 import json
 import os
@@ -17,24 +18,25 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "n
 
 
 def read(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-
-    def col(name, r):
-        i = hdr.index(name)
-        return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
-
+    """`path` is the --csv --log-file of `ncu --metrics ...` (one row per launch and metric)."""
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0] != "ID" and not r[0].startswith("==")]
     out = dict(launches=0, dram_bytes=0.0, warp_inst=0.0, thread_inst=0.0, time_s=0.0, kernels=[])
-    for r in rows[2:]:
-        out["launches"] += 1
-        out["dram_bytes"] += col("dram__bytes_read.sum", r) + col("dram__bytes_write.sum", r)
-        out["warp_inst"] += col("smsp__inst_executed.sum", r)
-        out["thread_inst"] += col("thread_inst_executed", r)
-        out["time_s"] += col("gpu__time_duration.sum", r)
-        k = r[hdr.index("Kernel Name")]
-        if k not in out["kernels"]:
-            out["kernels"].append(k)
+    ids = set()
+    for r in rows:
+        kid, kernel, metric, unit, value = r[0], r[4], r[-3], r[-2], float(r[-1].replace(",", ""))
+        value *= UNIT.get(unit, 1.0)
+        ids.add(kid)
+        if kernel not in out["kernels"]:
+            out["kernels"].append(kernel)
+        if metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            out["dram_bytes"] += value
+        elif metric == "smsp__inst_executed.sum":
+            out["warp_inst"] += value
+        elif metric == "smsp__thread_inst_executed.sum":
+            out["thread_inst"] += value
+        elif metric == "gpu__time_duration.sum":
+            out["time_s"] += value
+    out["launches"] = len(ids)
     return out
 
 
