@@ -359,6 +359,93 @@ A7_HD void cube_search_pruned_u8(const uint32_t *d, int n, const int *bits, cons
 		}
 }
 
+// Building blocks of the two-phase form of the pruned search used by the CUDA kernel (bc7amd.cu, cube_batch): phase A
+// sets up every lattice of an item (ramp tables, per-channel bounds, the seed corner), phase B evaluates the surviving
+// corners of ALL items of a batch as one evenly divided list of units.
+A7_HD void cube_floors(const real epa[2][4], const int *bits, int use_par, int fl[2][3][2]) {
+#pragma unroll 1
+	for (int e = 0; e < 2; e++)
+#pragma unroll 1
+		for (int k = 0; k < 3; k++)
+#pragma unroll 1
+			for (int par = 0; par <= use_par; par++) fl[e][k][par] = endpoint_floor(epa[e][k], bits[k], use_par, par);
+}
+// tab[k * 4 + x] = C ramp bytes of channel k for endpoint combination x; lb[k * 4 + x] = sum over the texels of the
+// smallest squared distance of channel k to that ramp
+template <int CLOG>
+A7_HD void cube_lattice_setup(const uint32_t *d, int n, const int *bits, const int fl[2][3][2], int use_par, int odd, int flip, uint64_t *tab,
+															uint32_t *lb, uint32_t *ep_packed) {
+	constexpr int C = 1 << CLOG;
+#pragma unroll 1
+	for (int k = 0; k < 3; k++) {
+		int ep[2][2];
+#pragma unroll
+		for (int e = 0; e < 2; e++) {
+			const int f = fl[e][k][(odd ^ (flip & e)) & 1];
+			const int top = (1 << bits[k]) - 1;
+			ep[e][0] = expand_bits(bits[k], f);
+			ep[e][1] = expand_bits(bits[k], f + ((top - f < (1 << use_par) ? top - f : (1 << use_par)) & ~use_par));
+		}
+		ep_packed[k] = (uint32_t) ep[0][0] | ((uint32_t) ep[0][1] << 8) | ((uint32_t) ep[1][0] << 16) | ((uint32_t) ep[1][1] << 24);
+#pragma unroll
+		for (int x = 0; x < 4; x++) {
+			uint64_t rv[1];
+			ramp_bytes<CLOG>(ep[0][x & 1], ep[1][x >> 1], rv);
+			tab[k * 4 + x] = rv[0];
+			uint32_t sum = 0;
+#pragma unroll 1
+			for (int i = 0; i < n; i++) {
+				const int v = (int) ((d[i] >> (8 * k)) & 255u);
+				int m = 255;
+#pragma unroll
+				for (int c = 0; c < C; c++) {
+					int a = (int) byte_of(rv[0], c) - v;
+					a = a < 0 ? -a : a;
+					m = a < m ? a : m;
+				}
+				sum += (uint32_t) (m * m);
+			}
+			lb[k * 4 + x] = sum;
+		}
+	}
+}
+// the ramp tables of a lattice from its packed expanded endpoints (see cube_lattice_setup)
+template <int CLOG> A7_HD void cube_tab_from_ep(const uint32_t *ep_packed, uint64_t *tab) {
+#pragma unroll 1
+	for (int k = 0; k < 3; k++) {
+		const uint32_t e = ep_packed[k];
+#pragma unroll
+		for (int x = 0; x < 4; x++) {
+			uint64_t rv[1];
+			ramp_bytes<CLOG>((int) ((e >> (8 * (x & 1))) & 255u), (int) ((e >> (16 + 8 * (x >> 1))) & 255u), rv);
+			tab[k * 4 + x] = rv[0];
+		}
+	}
+}
+A7_HD uint32_t cube_corner_bound(const uint32_t *lb, int corner) { return lb[corner & 3] + lb[4 + ((corner >> 2) & 3)] + lb[8 + (corner >> 4)]; }
+A7_HD int cube_seed_corner(const uint32_t *lb) { // smallest bound, first in (x, y, z) order
+	int sx = 0, sy = 0, sz = 0;
+#pragma unroll
+	for (int x = 1; x < 4; x++) {
+		if (lb[x] < lb[sx]) sx = x;
+		if (lb[4 + x] < lb[4 + sy]) sy = x;
+		if (lb[8 + x] < lb[8 + sz]) sz = x;
+	}
+	return sx | (sy << 2) | (sz << 4);
+}
+A7_HD uint64_t cube_survivors(const uint32_t *lb, uint32_t best_err) {
+	uint64_t mask = 0;
+#pragma unroll 1
+	for (int z = 0; z < 4; z++)
+#pragma unroll
+		for (int y = 0; y < 4; y++) {
+			const uint32_t t = lb[8 + z] + lb[4 + y];
+#pragma unroll
+			for (int x = 0; x < 4; x++) mask |= (uint64_t) (t + lb[x] <= best_err ? 1 : 0) << (x | (y << 2) | (z << 4));
+		}
+	return mask;
+}
+
 // ---- (q, p) re-indexings of a collapsed index set (the double loop of :1144-1146 / :835-836), as an ordered list
 A7_HD int qp_count(int Mi, int Mi_) {
 	int c = 0;
@@ -378,14 +465,15 @@ A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
 // lattice. key = err << 8 | lattice << 6 | gray position (minimum = first strict minimum in the reference's order).
 template <int CLOG>
 A7_HDN void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, const int *bits, int type, int z0, int z1, uint32_t &key,
-												uint64_t &idx) {
+												uint64_t &idx, bool prune = true) {
 	ClusterAcc<CLOG> cs;
 	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
 	real epa[2][4];
 	fit_endpoints_acc<CLOG>(cs, 3, epa);
 	key = 0xffffffffu;
 	idx = 0;
-	cube_search_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
+	if (prune) cube_search_pruned_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
+	else cube_search_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
 }
 
 // ep_shaker_d on packed 8-bit data (dimension 3). index_io in/out; returns the SSE (exact integer as real).
@@ -427,7 +515,7 @@ A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, con
 				fit_endpoints_acc<CLOG>(cs, 3, epa);
 				uint32_t key = 0xffffffffu;
 				uint64_t idx_1 = 0;
-				cube_search_u8<CLOG>(S.d, n, bits, epa, use_par, bcc, 0, 4, key, idx_1);
+				cube_search_pruned_u8<CLOG>(S.d, n, bits, epa, use_par, bcc, 0, 4, key, idx_1);
 				const uint32_t err_1 = key >> 8;
 				if (err_1 < err_2) {
 					err_2 = err_1;
