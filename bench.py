@@ -60,7 +60,7 @@ def _alu(cname, blocks_per_s, sm_mhz):
     ach = c["thread_inst_per_block"] * blocks_per_s
     return {"achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T lane-ops/s", "frac": ach / peak,
             "thread_inst_per_block": c["thread_inst_per_block"], "warp_inst_per_block": c["warp_inst_per_block"],
-            "lanes_per_inst": c["thread_inst_per_block"] / max(c["warp_inst_per_block"], 1.0), "source": "profiles/" + c["report"]}
+            "lanes_per_inst": c["thread_inst_per_block"] / max(c["warp_inst_per_block"], 1.0), "source": "profiles/ncu_counters/" + c["report"]}
 
 
 class ClockSampler:
@@ -408,7 +408,7 @@ def main():
                             "launches_per_step": int(launches) // max(args.steps, 1),
                             "note": "achieved / traffic / algorithmic bytes are per step (= per image: every launch of the step "
                                     "together; AMD BC7 is one launch per mode); traffic = ncu dram bytes per block of "
-                                    + (f"profiles/{ctr['report']} ({ctr['blocks']} blocks)" if ctr else "n/a") +
+                                    + (f"profiles/ncu_counters/{ctr['report']} ({ctr['blocks']} blocks)" if ctr else "n/a") +
                                     " x the blocks of this workload. The per-block search is ALU bound (SURVEY.md 8d): see `alu`"},
                "blocks_per_s": world * nblocks * args.steps / (total_ms_max / 1e3)}
         out["alu"] = _alu(cname, out["blocks_per_s"] / world, clk.get("sm_mhz"))

@@ -1,4 +1,4 @@
-// bc6h.cu -- sm_100a kernel for the AMD-Compressonator-compatible BC6H path (unsigned half sources).
+// bc6h.cu -- sm_100a kernel for the AMD-Compressonator-compatible BC6H path (unsigned and signed sources).
 //
 // Replaces the image loop of reference src/amd_bc6h_compressor.cpp:10-58 (gather via block_utils.cpp:7-41) and
 // BC6HBlockEncoder::CompressBlock (src/amd_bc6h_body.cpp:1521-1652); the search is bc6h_core.cuh.
@@ -37,6 +37,7 @@ struct Bc6Params {
 	SrcImage img;
 	uint4 *dst;
 	uint64_t n_blocks;
+	int is_signed;
 };
 
 __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 		ws.in[lane * 4 + 0] = t.x; ws.in[lane * 4 + 1] = t.y; ws.in[lane * 4 + 2] = t.z; ws.in[lane * 4 + 3] = t.w;
 	}
 	__syncwarp();
-	if (lane == 0) prepare_block(ws.in, false, ws.din);
+	if (lane == 0) prepare_block(ws.in, p.is_signed != 0, ws.din);
 	__syncwarp();
 	float din[16][4];
 	for (int i = 0; i < 16; i++)
@@ -63,11 +64,12 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 
 	// ---- shape phase
 	ShapeFit mine;
-	float e = fit_shape(din, 2, (int) lane, mine);
+	const bool sgn = p.is_signed != 0;
+	float e = fit_shape(din, 2, (int) lane, mine, sgn);
 	float gate = FLT_MAX;
 	if (lane == 0) {
 		ShapeFit one;
-		gate = fit_shape(din, 1, 0, one);
+		gate = fit_shape(din, 1, 0, one, sgn);
 	}
 	gate = __shfl_sync(FULL, gate, 0);
 	int who = (int) lane;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 		float err = FLT_MAX;
 		bool second = false;
 		const ShapeFit fit = ws.fit;
-		const bool fits = try_mode(din, fit, shape, (int) lane, err, second, ws.q[lane], ws.idx[lane]);
+		const bool fits = try_mode(din, fit, shape, (int) lane, err, second, ws.q[lane], ws.idx[lane], sgn);
 		ws.err[lane] = err;
 		ws.fits[lane] = fits ? 1 : 0;
 		ws.second[lane] = second ? 1 : 0;
@@ -124,9 +126,8 @@ cudaError_t init_bc6h_tables() {
 }
 
 cudaError_t launch_bc6h(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream) {
-	// Only the unsigned path is built (BASELINE config 4). Signed sources fail loudly rather than silently differ.
-	if (opts.bc6h_signed) return cudaErrorNotSupported;
 	Bc6Params p;
+	p.is_signed = opts.bc6h_signed ? 1 : 0;
 	p.img = img;
 	p.dst = static_cast<uint4 *>(dst);
 	p.n_blocks = (uint64_t) img.blocks_x * img.blocks_y * img.slices;

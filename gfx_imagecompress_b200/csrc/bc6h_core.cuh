@@ -110,11 +110,16 @@ H6_HD float lerp_weighted(float a, float b, int i, int denom) { // lerpf (:66-81
 	const int wa = denom == 7 ? w3[denom - i] : w4[denom - i], wb = denom == 7 ? w3[i] : w4[i];
 	return (a * (float) wa + b * (float) wb) / 64.0f;
 }
-H6_HD int quantize_to_int(int value, int prec) { // QuantizeToInt (:83-115), unsigned; `value` already a short
+// QuantizeToInt (:83-115); `value` already a short. Signed sources: one bit less, and the reference scales the ORIGINAL
+// (still negative) value before negating the quotient, so a negative endpoint quantises to a POSITIVE code -- kept.
+H6_HD int quantize_to_int(int value, int prec, bool is_signed) {
 	if (prec <= 1) return 0;
+	const bool neg = is_signed && value < 0;
+	if (is_signed) prec--;
 	int bias = (prec > 10 && prec != 16) ? ((1 << (prec - 11)) - 1) : 0;
 	bias = (prec == 16) ? 15 : bias;
-	return ((value << prec) + bias) / (0x7bff + 1);
+	const int q = (value * (1 << prec) + bias) / (0x7bff + 1);
+	return neg ? -q : q;
 }
 H6_HD int unquantize_u(int comp, int bits) { // Unquantize (:117-150), unsigned
 	if (bits >= 15) return comp;
@@ -498,7 +503,7 @@ H6_HD float shape_error(const float din[16][4], const float pal[2][16][3], int r
 }
 
 // FindBestPattern (:904-1037) without ep_shaker_HD. regions 1: all texels; regions 2: `shape`.
-H6_HDN float fit_shape(const float din[16][4], int regions, int shape, ShapeFit &F) {
+H6_HDN float fit_shape(const float din[16][4], int regions, int shape, ShapeFit &F, bool is_signed = false) {
 	const uint32_t mask = regions == 2 ? kShape[shape] : 0u;
 	float part[2][kMaxEntries][4];
 	F.count[0] = F.count[1] = 0;
@@ -529,9 +534,10 @@ H6_HDN float fit_shape(const float din[16][4], int regions, int shape, ShapeFit 
 #pragma unroll 1
 		for (int c = 0; c < 3; c++) {
 			float a = out[mini][c], b = out[maxi][c];
-			// clampF16Max (:506-528), unsigned
-			a = a < 0.0f ? 0.f : (a > 31743.f ? 31743.f : a);
-			b = b < 0.0f ? 0.f : (b > 31743.f ? 31743.f : b);
+			// clampF16Max (:506-528)
+			const float lo = is_signed ? -31743.f : 0.f;
+			a = a < lo ? lo : (a > 31743.f ? 31743.f : a);
+			b = b < lo ? lo : (b > 31743.f ? 31743.f : b);
 			F.ep[s][0][c] = a;
 			F.ep[s][1][c] = b;
 		}
@@ -545,13 +551,13 @@ H6_HDN float fit_shape(const float din[16][4], int regions, int shape, ShapeFit 
 }
 
 // ---- mode fitting (EncodePattern, two-region) ----------------------------------------------------------------
-H6_HD void quantise_endpoints(const float ep[2][2][3], int q[2][2][3], int prec) { // QuantizeEndPointToF16Prec (:536-548)
+H6_HD void quantise_endpoints(const float ep[2][2][3], int q[2][2][3], int prec, bool is_signed) { // QuantizeEndPointToF16Prec (:536-548)
 #pragma unroll 1
 	for (int s = 0; s < 2; s++)
 #pragma unroll 1
 		for (int e = 0; e < 2; e++)
 #pragma unroll 1
-			for (int c = 0; c < 3; c++) q[s][e][c] = quantize_to_int((int) (short) ep[s][e][c], prec);
+			for (int c = 0; c < 3; c++) q[s][e][c] = quantize_to_int((int) (short) ep[s][e][c], prec, is_signed);
 }
 H6_HD int subset1_fixup(int shape) { // g_Region2FixUp: position of the anchor inside subset 1's texel list
 	return __builtin_popcount(kShape[shape] & ((1u << kAnchor[shape]) - 1u));
@@ -592,20 +598,23 @@ H6_HD bool transform_endpoints(const ModeDesc &md, const int in[2][2][3], int ou
 	}
 	return true;
 }
-// decompress_endpts (:457-488), unsigned
-H6_HD void decode_endpoints(const ModeDesc &md, const int in[2][2][3], int out[2][2][3]) {
+// decompress_endpts (:457-488). Signed sources sign-extend; the transformed base endpoint is extended from
+// IndexPrec (= 3) bits in the reference (:465), kept.
+H6_HD void decode_endpoints(const ModeDesc &md, const int in[2][2][3], int out[2][2][3], bool is_signed) {
 #pragma unroll 1
 	for (int c = 0; c < 3; c++) {
-		out[0][0][c] = in[0][0][c];
 		if (md.transformed) {
 			const int mw = (1 << md.nbits) - 1;
-			out[0][1][c] = (sign_extend(in[0][1][c], md.prec[c]) + in[0][0][c]) & mw;
-			out[1][0][c] = (sign_extend(in[1][0][c], md.prec[c]) + in[0][0][c]) & mw;
-			out[1][1][c] = (sign_extend(in[1][1][c], md.prec[c]) + in[0][0][c]) & mw;
+			out[0][0][c] = is_signed ? sign_extend(in[0][0][c], 3) : in[0][0][c];
+#pragma unroll 1
+			for (int k = 1; k < 4; k++) {
+				const int t = (sign_extend(in[k >> 1][k & 1][c], md.prec[c]) + in[0][0][c]) & mw;
+				out[k >> 1][k & 1][c] = is_signed ? sign_extend(t, md.nbits) : t;
+			}
 		} else {
-			out[0][1][c] = in[0][1][c];
-			out[1][0][c] = in[1][0][c];
-			out[1][1][c] = in[1][1][c];
+			out[0][0][c] = is_signed ? sign_extend(in[0][0][c], md.nbits) : in[0][0][c];
+#pragma unroll 1
+			for (int k = 1; k < 4; k++) out[k >> 1][k & 1][c] = is_signed ? sign_extend(in[k >> 1][k & 1][c], md.prec[c]) : in[k >> 1][k & 1][c];
 		}
 	}
 }
@@ -620,38 +629,55 @@ struct Encoded {
 // One mode of EncodePattern (:1393-1478). Returns true if the mode fits; err = palette error after re-indexing,
 // second_fit = TransformEndPoints of the re-quantised decoded endpoints (decides whether the mode may win).
 H6_HDN bool try_mode(const float din[16][4], const ShapeFit &F, int shape, int mode, float &err, bool &second_fit, int q_out[2][2][3],
-										 int idx_out[2][kMaxEntries]) {
+										 int idx_out[2][kMaxEntries], bool is_signed = false) {
 	const ModeDesc md = mode_desc(mode);
 	int f16[2][2][3], idx[2][kMaxEntries];
 #pragma unroll 1
 	for (int s = 0; s < 2; s++)
 #pragma unroll 1
 		for (int k = 0; k < kMaxEntries; k++) idx[s][k] = F.idx[s][k];
-	quantise_endpoints(F.ep, f16, md.nbits);
+	quantise_endpoints(F.ep, f16, md.nbits, is_signed);
 	swap_indices(f16, idx, F.count, shape);
 	int q[2][2][3];
 	const bool tf = transform_endpoints(md, f16, q);
 	if (!tf) return false; // (`fits` is evaluated by the reference on the partial output, but both must hold)
 	int dec[2][2][3];
-	decode_endpoints(md, q, dec);
+	decode_endpoints(md, q, dec, is_signed);
 	bool fits = true;
 #pragma unroll 1
 	for (int s = 0; s < 2; s++)
 #pragma unroll 1
 		for (int c = 0; c < 3; c++) fits = fits && (f16[s][0][c] == dec[s][0][c]) && (f16[s][1][c] == dec[s][1][c]);
 	if (!fits) return false;
-	// decompress_endpoints2 (:1140-1252), unsigned path: unquantise + 31/64 scaling
+	// decompress_endpoints2 (:1140-1252): BC6H_data.issigned is never set, so ALWAYS the unsigned path, fed with the
+	// transformed fields: unquantise + 31/64 scaling
+	int udec[2][2][3];
+	decode_endpoints(md, q, udec, false);
 	float un[2][2][3];
 #pragma unroll 1
 	for (int s = 0; s < 2; s++)
 #pragma unroll 1
 		for (int e = 0; e < 2; e++)
 #pragma unroll 1
-			for (int c = 0; c < 3; c++) un[s][e][c] = (float) ((unquantize_u(dec[s][e][c], md.nbits) * 31) >> 6);
+			for (int c = 0; c < 3; c++) un[s][e][c] = (float) ((unquantize_u(udec[s][e][c], md.nbits) * 31) >> 6);
 	float pal[2][16][3];
 	build_palette(un, 2, pal);
-	// ReIndexShapef (:838-902)
 	const uint32_t mask = kShape[shape];
+	if (is_signed) { // no re-indexing, no second quantisation for signed sources (:1436, :1456)
+		err = shape_error(din, pal, 2, mask);
+		second_fit = true;
+#pragma unroll 1
+		for (int s = 0; s < 2; s++) {
+#pragma unroll 1
+			for (int e = 0; e < 2; e++)
+#pragma unroll 1
+				for (int c = 0; c < 3; c++) q_out[s][e][c] = q[s][e][c];
+#pragma unroll 1
+			for (int k = 0; k < kMaxEntries; k++) idx_out[s][k] = idx[s][k];
+		}
+		return true;
+	}
+	// ReIndexShapef (:838-902)
 	int pos[2] = {0, 0};
 #pragma unroll 1
 	for (int i = 0; i < 16; i++) {
@@ -667,7 +693,7 @@ H6_HDN bool try_mode(const float din[16][4], const ShapeFit &F, int shape, int m
 	}
 	err = shape_error(din, pal, 2, mask);
 	// what the reference does when this mode beats the running best (:1453-1459)
-	quantise_endpoints(un, f16, md.nbits);
+	quantise_endpoints(un, f16, md.nbits, false);
 	swap_indices(f16, idx, F.count, shape);
 	second_fit = transform_endpoints(md, f16, q_out);
 #pragma unroll 1
@@ -749,11 +775,11 @@ H6_HD void encode_block_serial(const float in[64], bool is_signed, uint64_t out[
 	float din[16][4];
 	prepare_block(in, is_signed, din);
 	ShapeFit best_fit, cur;
-	float best = fit_shape(din, 1, 0, cur); // the one-region error only gates the two-region scan (see header)
+	float best = fit_shape(din, 1, 0, cur, is_signed); // the one-region error only gates the two-region scan (see header)
 	int best_shape = -1;
 	if (!(best < FLT_MAX)) best = FLT_MAX;
 	for (int shape = 0; shape < 32; shape++) {
-		const float e = fit_shape(din, 2, shape, cur);
+		const float e = fit_shape(din, 2, shape, cur, is_signed);
 		if (e < best) {
 			best = e;
 			best_shape = shape;
@@ -771,7 +797,7 @@ H6_HD void encode_block_serial(const float in[64], bool is_signed, uint64_t out[
 	for (int m = 1; m <= 10; m++) {
 		err[m] = FLT_MAX;
 		second[m] = false;
-		fits[m] = try_mode(din, best_fit, shape, m, err[m], second[m], cand[m].q, cand[m].idx);
+		fits[m] = try_mode(din, best_fit, shape, m, err[m], second[m], cand[m].q, cand[m].idx, is_signed);
 	}
 	const int m = pick_mode(fits, err, second);
 	Encoded E;

@@ -89,3 +89,51 @@ def test_block_api_and_image_api(engine, ref):
     dst = engine.Image_CompressAMDBC6H(engine.Image(img, synth.FMT_RGBA16UF))
     assert dst is not None and (dst.width, dst.height) == (64, 32)
     assert np.array_equal(dst.blocks(16), want)
+
+
+def signed_cases(n: int = 32):
+    """(name, (H, W, 4) float32) for the signed path (any source that is "float && signed" in the reference's terms:
+    R16G16B16A16_SFLOAT / R32G32B32A32_SFLOAT, e.g. its own FloatRGBA test pattern)."""
+    rng = np.random.default_rng(5)
+    out = [("pattern_FloatRGBA", synth.pattern("FloatRGBA", n, n)[0].astype(np.float32))]
+    a = rng.normal(0, 2.0, (n, n, 4)).astype(np.float16).astype(np.float32)
+    a[..., 3] = 1
+    out.append(("gauss_plus_minus", a))
+    b = (rng.uniform(-1, 1, (n, n, 4)) * np.array([100, 1, 0.01, 1])).astype(np.float16).astype(np.float32)
+    out.append(("scaled_plus_minus", b))
+    out.append(("hdr_positive", synth.hdr_rgba16f(n, n, 4).astype(np.float32)))
+    return out
+
+
+def _ref_signed_blocks(ref, fb):
+    want = np.zeros((len(fb), 16), np.uint8)
+    for i, b in enumerate(fb):
+        b = np.ascontiguousarray(b)
+        ref.lib.ref_bc6h_block(b.ctypes.data, 1, 0xFF, want[i].ctypes.data)
+    return want
+
+
+def test_core_hostbuild_signed_matches_reference(ref):
+    import hostbuild
+    L = hostbuild.load()
+    for name, img in signed_cases(16):
+        fb = hdr_blocks(img)
+        got = hostbuild.bc6h_blocks(L, fb, True)
+        want = _ref_signed_blocks(ref, fb)
+        bad = np.flatnonzero((got != want).any(axis=1))
+        assert bad.size == 0, f"{name}: {bad.size}/{len(want)} blocks differ, first {bad[:5]}"
+
+
+@pytest.mark.gpu
+def test_signed_sources_match_reference(engine, ref):
+    """RGBA32F / RGBA16F sources take the reference's signed path (src/amd_bc6h_compressor.cpp:18-28)."""
+    for name, img in signed_cases(32):
+        img = np.ascontiguousarray(img, np.float32)
+        got = engine.encode_host(engine.BC6H, img, synth.FMT_RGBA32F)
+        want = ref.encode(BC6H, img, synth.FMT_RGBA32F)
+        bad = np.flatnonzero((got != want).any(axis=1))
+        assert bad.size == 0, f"{name}: {bad.size}/{len(want)} blocks differ, first {bad[:5]}"
+    p, f = synth.pattern("FloatRGBA", 64, 64)
+    dst = engine.Image_CompressAMDBC6H(engine.Image(p, f))
+    assert dst is not None and dst.format == 25  # DXBC6H_SFLOAT
+    assert np.array_equal(dst.blocks(16), ref.encode(BC6H, p, f))
