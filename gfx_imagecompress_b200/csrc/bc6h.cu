@@ -3,12 +3,15 @@
 // Replaces the image loop of reference src/amd_bc6h_compressor.cpp:10-58 (gather via block_utils.cpp:7-41) and
 // BC6HBlockEncoder::CompressBlock (src/amd_bc6h_body.cpp:1521-1652); the search is bc6h_core.cuh.
 //
-// Mapping: one warp per 4x4 block, candidates -> lanes.
-//   shape phase : lane s fits two-region shape s (partition, two optQuantAnD problems, end points, palette error);
-//                 the one-region fit, whose error only gates the scan in the reference, is a 33rd task on lane 0
-//   selection   : lexicographic (error, shape) arg-min by warp shuffles = the reference's first strict minimum
-//   mode phase  : lanes 0..9 try the ten two-region modes on the winning shape; lane 0 replays the reference's
-//                 in-order scan over their results and packs the block
+// Mapping: one warp per group of kGroup = 4 consecutive 4x4 blocks, candidates -> lanes.
+//   shape phase : per block, lane s fits two-region shape s (partition, two optQuantAnD problems, end points, palette
+//                 error); lexicographic (error, shape) arg-min by warp shuffles = the reference's first strict minimum
+//   gate phase  : the one-region fit, whose error only gates the scan in the reference, for the group's 4 blocks on
+//                 lanes 0..3 at once (one lane per block would otherwise idle the warp for a third of its time)
+//   mode phase  : the 4 x 10 (block, two-region mode) trials spread over the lanes; lanes 0..3 then replay the
+//                 reference's in-order scan over their block's results and pack it
+// The quantiser reads the block channel-major from shared memory and keeps its work arrays lane-strided in shared
+// memory; palettes live in registers: no local-memory arrays in the shape phase.
 // FP32 in the reference's operation order, --fmad=false: blocks are bit-identical to the reference on every test
 // input (its qsort tie order can only differ on exactly equal projections).
 #include "common.cuh"
@@ -22,15 +25,23 @@ namespace {
 using namespace bc6;
 
 constexpr int kWarps = 4;
+constexpr int kGroup = 4;
 
-struct WarpScratch {
+struct BlockScratch {
 	float in[64];
 	float din[16][4];
-	ShapeFit fit;
+	float pxc[48];
+	ShapeFit fit, fit31; // best two-region shape / shape 31 (what the reference encodes when the one-region fit wins)
+	float emin;
+	int who, shape;
 	float err[11];
 	int fits[11], second[11];
 	int q[11][2][2][3];
 	int idx[11][2][kMaxEntries];
+};
+struct WarpScratch {
+	BlockScratch b[kGroup];
+	float work[2][kMaxEntries][32]; // lane-strided quantiser work arrays (QuantIOF)
 };
 
 struct Bc6Params {
@@ -44,78 +55,95 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint64_t block = (uint64_t) blockIdx.x * kWarps + warp;
-	if (block >= p.n_blocks) return; // whole warp
+	const uint64_t first = ((uint64_t) blockIdx.x * kWarps + warp) * kGroup;
+	if (first >= p.n_blocks) return; // whole warp
+	const int nb = (int) (p.n_blocks - first < (uint64_t) kGroup ? p.n_blocks - first : (uint64_t) kGroup);
 	WarpScratch &ws = scratch[warp];
+	const bool sgn = p.is_signed != 0;
 	const uint64_t per_slice = (uint64_t) p.img.blocks_x * p.img.blocks_y;
-	const uint32_t slice = (uint32_t) (block / per_slice);
-	const uint32_t rem = (uint32_t) (block - (uint64_t) slice * per_slice);
-	const uint32_t by = rem / p.img.blocks_x, bx = rem - by * p.img.blocks_x;
-	if (lane < 16) {
-		const float4 t = fetch_rgba(p.img, block, bx, by, slice, (int) lane);
-		ws.in[lane * 4 + 0] = t.x; ws.in[lane * 4 + 1] = t.y; ws.in[lane * 4 + 2] = t.z; ws.in[lane * 4 + 3] = t.w;
+	// ---- gather (replicate-edge clamp inside fetch_rgba), 16 texels per block
+	for (int t = (int) lane; t < nb * 16; t += 32) {
+		const int b = t >> 4, i = t & 15;
+		const uint64_t block = first + b;
+		const uint32_t slice = (uint32_t) (block / per_slice);
+		const uint32_t rem = (uint32_t) (block - (uint64_t) slice * per_slice);
+		const uint32_t by = rem / p.img.blocks_x, bx = rem - by * p.img.blocks_x;
+		const float4 v = fetch_rgba(p.img, block, bx, by, slice, i);
+		ws.b[b].in[i * 4 + 0] = v.x; ws.b[b].in[i * 4 + 1] = v.y; ws.b[b].in[i * 4 + 2] = v.z; ws.b[b].in[i * 4 + 3] = v.w;
 	}
 	__syncwarp();
-	if (lane == 0) prepare_block(ws.in, p.is_signed != 0, ws.din);
+	if ((int) lane < nb) prepare_block(ws.b[lane].in, sgn, ws.b[lane].din, ws.b[lane].pxc);
 	__syncwarp();
-	float din[16][4];
-	for (int i = 0; i < 16; i++)
-		for (int j = 0; j < 4; j++) din[i][j] = ws.din[i][j];
+	float *proj = &ws.work[0][0][lane], *dev = &ws.work[1][0][lane];
 
 	// ---- shape phase
-	ShapeFit mine;
-	const bool sgn = p.is_signed != 0;
-	float e = fit_shape(din, 2, (int) lane, mine, sgn);
-	float gate = FLT_MAX;
-	if (lane == 0) {
-		ShapeFit one;
-		gate = fit_shape(din, 1, 0, one, sgn);
+	for (int b = 0; b < nb; b++) {
+		ShapeFit mine;
+		const float e = fit_shape(ws.b[b].pxc, 2, (int) lane, mine, sgn, proj, dev, 32);
+		int who = (int) lane;
+		float emin = e;
+		for (int d = 16; d > 0; d >>= 1) {
+			const float e2 = __shfl_xor_sync(FULL, emin, d);
+			const int w2 = __shfl_xor_sync(FULL, who, d);
+			if (e2 < emin || (e2 == emin && w2 < who)) { emin = e2; who = w2; }
+		}
+		if ((int) lane == who) ws.b[b].fit = mine;
+		if (lane == 31) {
+			ws.b[b].fit31 = mine;
+			ws.b[b].emin = emin;
+			ws.b[b].who = who;
+		}
 	}
-	gate = __shfl_sync(FULL, gate, 0);
-	int who = (int) lane;
-	float emin = e;
-	for (int d = 16; d > 0; d >>= 1) {
-		const float e2 = __shfl_xor_sync(FULL, emin, d);
-		const int w2 = __shfl_xor_sync(FULL, who, d);
-		if (e2 < emin || (e2 == emin && w2 < who)) { emin = e2; who = w2; }
-	}
-	// the reference keeps the one-region fit only as a gate: if nothing beats it, the LAST shape's state is encoded
-	const int shape = (emin < gate) ? who : 31;
-	if ((int) lane == shape) ws.fit = mine;
 	__syncwarp();
-
+	// ---- gate phase: the reference keeps the one-region fit only as a gate; if nothing beats it, the LAST shape's
+	// state is encoded
+	if ((int) lane < nb) {
+		BlockScratch &B = ws.b[lane];
+		ShapeFit one;
+		const float gate = fit_shape(B.pxc, 1, 0, one, sgn, proj, dev, 32);
+		if (B.emin < gate) {
+			B.shape = B.who;
+		} else {
+			B.shape = 31;
+			B.fit = B.fit31;
+		}
+	}
+	__syncwarp();
 	// ---- mode phase
-	if (lane >= 1 && lane <= 10) {
+	for (int t = (int) lane; t < nb * 10; t += 32) {
+		const int b = t / 10, mode = t - b * 10 + 1;
+		BlockScratch &B = ws.b[b];
 		float err = FLT_MAX;
 		bool second = false;
-		const ShapeFit fit = ws.fit;
-		const bool fits = try_mode(din, fit, shape, (int) lane, err, second, ws.q[lane], ws.idx[lane], sgn);
-		ws.err[lane] = err;
-		ws.fits[lane] = fits ? 1 : 0;
-		ws.second[lane] = second ? 1 : 0;
+		const ShapeFit fit = B.fit;
+		const bool fits = try_mode(B.din, fit, B.shape, mode, err, second, B.q[mode], B.idx[mode], sgn);
+		B.err[mode] = err;
+		B.fits[mode] = fits ? 1 : 0;
+		B.second[mode] = second ? 1 : 0;
 	}
 	__syncwarp();
-	if (lane == 0) {
+	if ((int) lane < nb) {
+		BlockScratch &B = ws.b[lane];
 		bool fits[11], second[11];
 		float err[11];
 		for (int m = 1; m <= 10; m++) {
-			fits[m] = ws.fits[m] != 0;
-			second[m] = ws.second[m] != 0;
-			err[m] = ws.err[m];
+			fits[m] = B.fits[m] != 0;
+			second[m] = B.second[m] != 0;
+			err[m] = B.err[m];
 		}
 		Encoded E;
 		E.mode = pick_mode(fits, err, second);
-		E.shape = shape;
+		E.shape = B.shape;
 		if (E.mode) {
 			for (int s = 0; s < 2; s++)
 				for (int ee = 0; ee < 2; ee++)
-					for (int c = 0; c < 3; c++) E.q[s][ee][c] = ws.q[E.mode][s][ee][c];
+					for (int c = 0; c < 3; c++) E.q[s][ee][c] = B.q[E.mode][s][ee][c];
 			for (int s = 0; s < 2; s++)
-				for (int k = 0; k < kMaxEntries; k++) E.idx[s][k] = ws.idx[E.mode][s][k];
+				for (int k = 0; k < kMaxEntries; k++) E.idx[s][k] = B.idx[E.mode][s][k];
 		}
 		uint64_t out[2];
 		pack_block(E, out);
-		p.dst[block] = make_uint4((uint32_t) out[0], (uint32_t) (out[0] >> 32), (uint32_t) out[1], (uint32_t) (out[1] >> 32));
+		p.dst[first + lane] = make_uint4((uint32_t) out[0], (uint32_t) (out[0] >> 32), (uint32_t) out[1], (uint32_t) (out[1] >> 32));
 	}
 }
 
@@ -132,7 +160,7 @@ cudaError_t launch_bc6h(const SrcImage &img, const b200ic_opts &opts, void *dst,
 	p.dst = static_cast<uint4 *>(dst);
 	p.n_blocks = (uint64_t) img.blocks_x * img.blocks_y * img.slices;
 	if (p.n_blocks == 0) return cudaSuccess;
-	const uint64_t grid = (p.n_blocks + kWarps - 1) / kWarps;
+	const uint64_t grid = (p.n_blocks + (uint64_t) kWarps * kGroup - 1) / ((uint64_t) kWarps * kGroup);
 	bc6h_kernel<<<(unsigned) grid, kWarps * 32, kWarps * sizeof(WarpScratch), stream>>>(p);
 	return cudaGetLastError();
 }

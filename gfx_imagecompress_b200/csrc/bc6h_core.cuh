@@ -130,18 +130,26 @@ H6_HD int unquantize_u(int comp, int bits) { // Unquantize (:117-150), unsigned
 H6_HD int sign_extend(int w, int bits) { return ((w & (1 << (bits - 1))) ? ((~0) << bits) : 0) | w; }
 
 // ---- quantiser (optQuantAnD_f) -----------------------------------------------------------------------------
-H6_HD void sort_order_f(const float *key, int *order, int n) { // stable ascending, comparator a - b > 0
+// A quantiser call reads its n points straight from the block (channel-major: the 32 lanes of a warp, each fitting
+// another shape of the same block, hit 16 different banks or broadcast) and keeps its two n-element work arrays in
+// caller-provided storage: lane-strided shared memory on the GPU (element k at [k * stride]), local arrays on the host.
+struct QuantIOF {
+	const float *px;   // px[channel * 16 + texel]: texel values as the encoder sees them (prepare_block)
+	uint64_t texels;   // 4 bits per entry: texel of entry k
+	float *proj, *dev; // work arrays
+	int stride;
+};
+H6_HD float quant_point(const QuantIOF &io, int k, int j) { return io.px[j * 16 + (int) ((io.texels >> (4 * k)) & 15u)]; }
+H6_HD uint64_t texels_of_mask(uint32_t mask16, int &n) { // entries in texel order
+	uint64_t t = 0;
+	n = 0;
 #pragma unroll 1
-	for (int i = 0; i < n; i++) {
-		const float k = key[i];
-		int rank = 0;
-#pragma unroll 1
-		for (int j = 0; j < n; j++) {
-			const float kj = key[j];
-			rank += ((k - kj > 0) || (!(kj - k > 0) && j < i)) ? 1 : 0;
+	for (int i = 0; i < 16; i++)
+		if (mask16 & (1u << i)) {
+			t |= (uint64_t) i << (4 * n);
+			n++;
 		}
-		order[rank] = i;
-	}
+	return t;
 }
 
 // eigenVector_d (:1200-1286) in FP32: 4 rounds of (normalise, 5 squarings); symmetric, upper triangle only
@@ -207,105 +215,161 @@ H6_HDN void dominant_axis3(const float cov[3][3], float axis[3]) {
 	for (int i = 0; i < 3; i++) axis[i] /= t;
 }
 
-// quant_AnD_Shell (:1349-1425), FP32 clone (first assignment truncates an UNfloored value)
-H6_HDN void lattice_quantise_f(const float *v_, int k, int n, int *idx) {
-	float m = v_[0], M = v_[0];
+// quant_AnD_Shell (:1349-1425), FP32 clone (first assignment truncates an UNfloored value); io.proj[] in, packed
+// indices out (4 bits per entry)
+H6_HDN uint64_t lattice_quantise_f(const QuantIOF &io, int k, int n) {
+	const int st = io.stride;
+	float m = io.proj[0], M = m;
 #pragma unroll 1
 	for (int i = 1; i < n; i++) {
-		m = m < v_[i] ? m : v_[i];
-		M = M > v_[i] ? M : v_[i];
+		const float v = io.proj[i * st];
+		m = m < v ? m : v;
+		M = M > v ? M : v;
 	}
-	if (M == m) {
-#pragma unroll 1
-		for (int i = 0; i < n; i++) idx[i] = 0;
-		return;
-	}
+	if (M == m) return 0;
 	const float s = (float) (k - 1) / (M - m);
-	float d[kMaxEntries];
 	float dm = 0, r = 0;
+	uint64_t z4 = 0;
 #pragma unroll 1
 	for (int i = 0; i < n; i++) {
-		const float v = v_[i] * s;
+		const float v = io.proj[i * st] * s;
 		const float z = v + 0.5f - m * s;
-		idx[i] = (int) z;
-		d[i] = v - z - m * s;
-		dm += d[i];
-		r += d[i] * d[i];
+		z4 |= (uint64_t) ((int) z & 15) << (4 * i);
+		const float d = v - z - m * s;
+		io.dev[i * st] = d;
+		dm += d;
+		r += d * d;
 	}
+	uint32_t inc = 0;
 	if ((float) n * r - dm * dm >= (float) (n - 1) / 4 / 2) {
 		dm /= (float) n;
 #pragma unroll 1
-		for (int i = 0; i < n; i++) d[i] -= dm;
-		int ord[kMaxEntries];
-		sort_order_f(d, ord, n);
+		for (int i = 0; i < n; i++) io.dev[i * st] -= dm;
+		uint64_t ord = 0; // stable rank of every deviation (comparator a - b > 0)
+#pragma unroll 1
+		for (int i = 0; i < n; i++) {
+			const float ki = io.dev[i * st];
+			int rank = 0;
+#pragma unroll 1
+			for (int j = 0; j < n; j++) {
+				const float kj = io.dev[j * st];
+				rank += ((ki - kj > 0) || (!(kj - ki > 0) && j < i)) ? 1 : 0;
+			}
+			ord |= (uint64_t) i << (4 * rank);
+		}
 		float mm = 0, l = 0;
 		int j = -1;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
-			l += d[ord[i]] - (2.0f * (float) i + 1.0f - (float) n) / 2.0f / (float) n;
+			l += io.dev[(int) ((ord >> (4 * i)) & 15u) * st] - (2.0f * (float) i + 1.0f - (float) n) / 2.0f / (float) n;
 			if (l < mm) { mm = l; j = i; }
 		}
 		j = (j + 1) % n;
 #pragma unroll 1
-		for (int i = j; i < n; i++) idx[ord[i]]++;
+		for (int i = j; i < n; i++) inc |= 1u << (int) ((ord >> (4 * i)) & 15u);
 	}
-	int mi = idx[0];
+	int mi = 99;
 #pragma unroll 1
-	for (int i = 1; i < n; i++) mi = mi < idx[i] ? mi : idx[i];
+	for (int i = 0; i < n; i++) {
+		const int v = (int) ((z4 >> (4 * i)) & 15u) + (int) ((inc >> i) & 1u);
+		mi = mi < v ? mi : v;
+	}
+	uint64_t out = 0;
 #pragma unroll 1
-	for (int i = 0; i < n; i++) idx[i] -= mi;
+	for (int i = 0; i < n; i++) {
+		const int v = (int) ((z4 >> (4 * i)) & 15u) + (int) ((inc >> i) & 1u) - mi;
+		out |= (uint64_t) (v & 15) << (4 * i);
+	}
+	return out;
 }
 
-// optQuantAnD_f (:1427-1601), dimension 3, maxTry 4000. out[][3] = points on the fitted ramp; returns the SSE.
-H6_HDN float quantise_subset_f(const float data[][4], int n, int clusters, int *index, float out[][3]) {
-	if (n == 0) return 0.f;
-	float cen[kMaxEntries][3], mean[3], cov[3][3];
+// refit (:1500-1540): direction through the index-weighted centred points, projections into io.proj; s, t out
+H6_HD void quant_refit_f(const QuantIOF &io, const float *mean, int n, uint64_t a, bool want_st, float &s, float &t) {
+	float dir[3] = {0.f, 0.f, 0.f}, q = 0, ss = 0, tt = 0;
 #pragma unroll 1
-	for (int j = 0; j < 3; j++) {
-		float m = 0;
-#pragma unroll 1
-		for (int k = 0; k < n; k++) m += data[k][j];
-		m /= (float) n;
-		mean[j] = m;
-#pragma unroll 1
-		for (int k = 0; k < n; k++) cen[k][j] = data[k][j] - m;
+	for (int k = 0; k < n; k++) {
+		const int ik = (int) ((a >> (4 * k)) & 15u);
+		ss += (float) ik;
+		tt += (float) (ik * ik);
+#pragma unroll
+		for (int j = 0; j < 3; j++) dir[j] += (quant_point(io, k, j) - mean[j]) * (float) ik;
 	}
-#pragma unroll 1
-	for (int i = 0; i < 3; i++)
-#pragma unroll 1
-		for (int j = 0; j <= i; j++) {
-			float c = 0;
-#pragma unroll 1
-			for (int k = 0; k < n; k++) c += cen[k][i] * cen[k][j];
-			cov[i][j] = c;
-			cov[j][i] = c;
-		}
-	float dir[3] = {0.f, 0.f, 0.f}, proj[kMaxEntries];
-	dominant_axis3(cov, dir);
+#pragma unroll
+	for (int j = 0; j < 3; j++) q += dir[j] * dir[j];
+	if (want_st) {
+		ss /= (float) n;
+		tt = tt - ss * ss * (float) n;
+		tt = (tt == 0.0f ? 0.0f : 1.0f / tt);
+	}
+	q = sqrtf(q);
+	if (want_st) tt *= q;
+	if (q != 0)
+#pragma unroll
+		for (int j = 0; j < 3; j++) dir[j] /= q;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
 		float p = 0;
+#pragma unroll
+		for (int j = 0; j < 3; j++) p += (quant_point(io, k, j) - mean[j]) * dir[j];
+		io.proj[k * io.stride] = p;
+	}
+	s = ss;
+	t = tt;
+}
+
+// optQuantAnD_f (:1427-1601), dimension 3, maxTry 4000, followed by GetEndPoints (:1116-1159): returns the packed
+// indices; lo / hi = the points of the fitted ramp with the smallest / largest channel sum.
+H6_HDN uint64_t quantise_points_f(const QuantIOF &io, int n, int clusters, float lo[3], float hi[3]) {
+	const int st = io.stride;
+	float mean[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
-		for (int i = 0; i < 3; i++) p += cen[k][i] * dir[i];
-		proj[k] = p;
+	for (int k = 0; k < n; k++)
+#pragma unroll
+		for (int j = 0; j < 3; j++) mean[j] += quant_point(io, k, j);
+#pragma unroll
+	for (int j = 0; j < 3; j++) mean[j] /= (float) n;
+	float cov[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll 1
+	for (int k = 0; k < n; k++) {
+		float c[3];
+#pragma unroll
+		for (int j = 0; j < 3; j++) c[j] = quant_point(io, k, j) - mean[j];
+#pragma unroll
+		for (int i = 0; i < 3; i++)
+#pragma unroll
+			for (int j = 0; j <= i; j++) cov[i][j] += c[i] * c[j];
+	}
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+#pragma unroll
+		for (int j = 0; j < i; j++) cov[j][i] = cov[i][j];
+	{
+		float dir[3] = {0.f, 0.f, 0.f};
+		dominant_axis3(cov, dir);
+#pragma unroll 1
+		for (int k = 0; k < n; k++) {
+			float p = 0;
+#pragma unroll
+			for (int j = 0; j < 3; j++) p += (quant_point(io, k, j) - mean[j]) * dir[j];
+			io.proj[k * st] = p;
+		}
 	}
 	// The iteration of the reference (:1494-1575). Both steps are pure functions of the index vector -- refit+reassign F and
 	// the lattice quantiser G of the refit's projections -- so the state is one packed word `cur`, F / G are memoised on
-	// it, and once the state after G repeats one of the last 8 states with try_two unchanged (or already negative) the
-	// remaining iterations are periodic with a convergence test that keeps failing: the state after iteration 3999 is
-	// read from the history (see bc7amd_core.cuh quantise_subset; maxTry is 4000 here, so this is most of the saving).
-	uint64_t memo_key[4], memo_f[4], memo_g[4];
-	int memo_gvalid[4] = {0, 0, 0, 0}, memo_n = 0, memo_next = 0;
+	// it (four register slots), and once the state after G repeats one of the last 8 states with try_two unchanged (or
+	// already negative) the remaining iterations are periodic with a convergence test that keeps failing: the state after
+	// iteration 3999 is read from the history (see bc7amd_core.cuh; maxTry is 4000 here, so this is most of the saving).
+	uint64_t mk0 = 0, mk1 = 0, mk2 = 0, mk3 = 0, mf0 = 0, mf1 = 0, mf2 = 0, mf3 = 0, mg0 = 0, mg1 = 0, mg2 = 0, mg3 = 0;
+	uint32_t gvalid = 0;
+	int memo_n = 0, memo_next = 0;
 	constexpr int kHist = 8;
 	uint64_t hist[kHist];
 	int hist_try[kHist];
-	uint64_t first = 0, cur = 0;
+	uint64_t first = 0;
 	int try_two = 50;
 	float s, t;
 	H6_STATS_G();
-	lattice_quantise_f(proj, clusters, n, index); // iteration 0
-#pragma unroll 1
-	for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
+	uint64_t cur = lattice_quantise_f(io, clusters, n); // iteration 0
 	int it = 1;
 #pragma unroll 1
 	for (; it < kQuantMaxTry; it++) {
@@ -315,67 +379,35 @@ H6_HDN float quantise_subset_f(const float data[][4], int n, int clusters, int *
 		do {
 			const uint64_t a = cur;
 			int slot = -1;
-#pragma unroll 1
-			for (int m = 0; m < memo_n; m++)
-				if (memo_key[m] == a) slot = m;
+			if (memo_n > 0 && mk0 == a) slot = 0;
+			if (memo_n > 1 && mk1 == a) slot = 1;
+			if (memo_n > 2 && mk2 == a) slot = 2;
+			if (memo_n > 3 && mk3 == a) slot = 3;
 			uint64_t b;
 			if (slot >= 0) {
 				H6_STATS_REPLAY();
-				b = memo_f[slot];
+				b = slot == 0 ? mf0 : (slot == 1 ? mf1 : (slot == 2 ? mf2 : mf3));
 				have_proj = false;
 			} else {
 				H6_STATS_F();
-				float q = 0;
-				s = t = 0;
-#pragma unroll 1
-				for (int k = 0; k < n; k++) {
-					index[k] = (int) ((a >> (4 * k)) & 15u);
-					s += (float) index[k];
-					t += (float) (index[k] * index[k]);
-				}
-#pragma unroll 1
-				for (int j = 0; j < 3; j++) {
-					float d = 0;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) d += cen[k][j] * (float) index[k];
-					dir[j] = d;
-					q += d * d;
-				}
-				s /= (float) n;
-				t = t - s * s * (float) n;
-				t = (t == 0.0f ? 0.0f : 1.0f / t);
-				q = sqrtf(q);
-				t *= q;
-				if (q != 0)
-#pragma unroll 1
-					for (int j = 0; j < 3; j++) dir[j] /= q;
-#pragma unroll 1
-				for (int k = 0; k < n; k++) {
-					float p = 0;
-#pragma unroll 1
-					for (int i = 0; i < 3; i++) p += cen[k][i] * dir[i];
-					proj[k] = p;
-				}
+				quant_refit_f(io, mean, n, a, true, s, t);
 				// boundaries (k + 0.5 - s) * t are evaluated in double by the reference's mixed expression (:1549);
 				// they are non-decreasing in k, so the running-k walk over sorted projections == counting
-				double bound[15];
-#pragma unroll 1
-				for (int k = 0; k < clusters - 1; k++) bound[k] = ((double) k + 0.5 - (double) s) * (double) t;
 				b = 0;
 #pragma unroll 1
-				for (int j = 0; j < n; j++) {
-					const double pj = (double) proj[j];
-					int k = 0;
+				for (int c = 0; c < clusters - 1; c++) {
+					const double bound = ((double) c + 0.5 - (double) s) * (double) t;
 #pragma unroll 1
-					for (int c = 0; c < clusters - 1; c++) k += (pj > bound[c]) ? 1 : 0;
-					b |= (uint64_t) k << (4 * j);
+					for (int j = 0; j < n; j++) b += (uint64_t) ((double) io.proj[j * st] > bound ? 1 : 0) << (4 * j);
 				}
 				slot = memo_next;
 				memo_next = (memo_next + 1) & 3;
 				memo_n = memo_n < 4 ? memo_n + 1 : 4;
-				memo_key[slot] = a;
-				memo_f[slot] = b;
-				memo_gvalid[slot] = 0;
+				if (slot == 0) { mk0 = a; mf0 = b; }
+				else if (slot == 1) { mk1 = a; mf1 = b; }
+				else if (slot == 2) { mk2 = a; mf2 = b; }
+				else { mk3 = a; mf3 = b; }
+				gvalid &= ~(1u << slot);
 				have_proj = true;
 			}
 			cur = b;
@@ -384,39 +416,21 @@ H6_HDN float quantise_subset_f(const float data[][4], int n, int clusters, int *
 		} while (!done && try_two--);
 		if (it == 1) first = cur;
 		else if (first == cur) { H6_STATS_IT(it); break; }
-		if (memo_gvalid[last]) {
-			cur = memo_g[last];
+		if ((gvalid >> last) & 1u) {
+			cur = last == 0 ? mg0 : (last == 1 ? mg1 : (last == 2 ? mg2 : mg3));
 		} else {
 			if (!have_proj) {
-				const uint64_t a = memo_key[last];
-				float q = 0;
-#pragma unroll 1
-				for (int j = 0; j < 3; j++) {
-					float d = 0;
-#pragma unroll 1
-					for (int k = 0; k < n; k++) d += cen[k][j] * (float) (int) ((a >> (4 * k)) & 15u);
-					dir[j] = d;
-					q += d * d;
-				}
-				q = sqrtf(q);
-				if (q != 0)
-#pragma unroll 1
-					for (int j = 0; j < 3; j++) dir[j] /= q;
-#pragma unroll 1
-				for (int k = 0; k < n; k++) {
-					float p = 0;
-#pragma unroll 1
-					for (int i = 0; i < 3; i++) p += cen[k][i] * dir[i];
-					proj[k] = p;
-				}
+				const uint64_t a = last == 0 ? mk0 : (last == 1 ? mk1 : (last == 2 ? mk2 : mk3));
+				float s2, t2;
+				quant_refit_f(io, mean, n, a, false, s2, t2);
 			}
 			H6_STATS_G();
-			lattice_quantise_f(proj, clusters, n, index);
-			cur = 0;
-#pragma unroll 1
-			for (int k = 0; k < n; k++) cur |= (uint64_t) (index[k] & 15) << (4 * k);
-			memo_g[last] = cur;
-			memo_gvalid[last] = 1;
+			cur = lattice_quantise_f(io, clusters, n);
+			if (last == 0) mg0 = cur;
+			else if (last == 1) mg1 = cur;
+			else if (last == 2) mg2 = cur;
+			else mg3 = cur;
+			gvalid |= 1u << last;
 		}
 		if (it >= 2) {
 			int period = 0;
@@ -436,40 +450,44 @@ H6_HDN float quantise_subset_f(const float data[][4], int n, int clusters, int *
 		hist_try[(it + 1) & (kHist - 1)] = try_two;
 		if (it == kQuantMaxTry - 1) { H6_STATS_IT(kQuantMaxTry); }
 	}
-#pragma unroll 1
-	for (int k = 0; k < n; k++) index[k] = (int) ((cur >> (4 * k)) & 15u);
+	// the ramp points (:1578-1600) and, of those, the ones with the smallest / largest channel sum (GetEndPoints)
+	float dir[3] = {0.f, 0.f, 0.f};
 	s = t = 0;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
-		s += (float) index[k];
-		t += (float) (index[k] * index[k]);
-	}
-#pragma unroll 1
-	for (int j = 0; j < 3; j++) {
-		float d = 0;
-#pragma unroll 1
-		for (int k = 0; k < n; k++) d += cen[k][j] * (float) index[k];
-		dir[j] = d;
+		const int ik = (int) ((cur >> (4 * k)) & 15u);
+		s += (float) ik;
+		t += (float) (ik * ik);
+#pragma unroll
+		for (int j = 0; j < 3; j++) dir[j] += (quant_point(io, k, j) - mean[j]) * (float) ik;
 	}
 	s /= (float) n;
 	t = t - s * s * (float) n;
 	t = (t == 0.0f ? 0.0f : 1.0f / t);
-	float err = 0;
+	float mn = 65504.0f, mx = 0.f;
 #pragma unroll 1
-	for (int i = 0; i < n; i++)
-#pragma unroll 1
+	for (int i = 0; i < n; i++) {
+		const int ii = (int) ((cur >> (4 * i)) & 15u);
+		float o[3];
+#pragma unroll
+		for (int j = 0; j < 3; j++) o[j] = mean[j] + dir[j] * t * ((float) ii - s);
+		const float v = o[0] + o[1] + o[2];
+		const bool first_entry = i == 0, lower = v < mn, higher = v > mx; // mini = maxi = 0 unless a strict improvement
+		mn = lower ? v : mn;
+		mx = higher ? v : mx;
+#pragma unroll
 		for (int j = 0; j < 3; j++) {
-			const float o = mean[j] + dir[j] * t * ((float) index[i] - s);
-			out[i][j] = o;
-			err += (data[i][j] - o) * (data[i][j] - o);
+			lo[j] = (first_entry || lower) ? o[j] : lo[j];
+			hi[j] = (first_entry || higher) ? o[j] : hi[j];
 		}
-	return err;
+	}
+	return cur;
 }
 
 // ---- shape evaluation ---------------------------------------------------------------------------------------
 struct ShapeFit {
 	float ep[2][2][3]; // [subset][A/B][rgb] endpoints in half-code units
-	int idx[2][kMaxEntries];
+	uint64_t idx[2];   // quantiser indices per subset, 4 bits per entry
 	int count[2];
 };
 
@@ -501,53 +519,76 @@ H6_HD float shape_error(const float din[16][4], const float pal[2][16][3], int r
 	}
 	return total;
 }
-
-// FindBestPattern (:904-1037) without ep_shaker_HD. regions 1: all texels; regions 2: `shape`.
-H6_HDN float fit_shape(const float din[16][4], int regions, int shape, ShapeFit &F, bool is_signed = false) {
-	const uint32_t mask = regions == 2 ? kShape[shape] : 0u;
-	float part[2][kMaxEntries][4];
-	F.count[0] = F.count[1] = 0;
+// The same two steps for the shape scan with the palette in REGISTERS (every index static): entry j of subset `sub` is
+// recomputed from the end points where it is needed, the early-exit scan becomes a flag.  pxc = channel-major block.
+template <int REGIONS> H6_HD float shape_error_direct(const float *pxc, const float ep[2][2][3], uint32_t mask) {
+	constexpr int NP = REGIONS == 1 ? 16 : 8;
+	float pal[REGIONS][NP][3];
+#pragma unroll
+	for (int r = 0; r < REGIONS; r++)
+#pragma unroll
+		for (int j = 0; j < NP; j++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) pal[r][j][c] = lerp_weighted(ep[r][0][c], ep[r][1][c], j, NP - 1);
+	float total = 0.f;
 #pragma unroll 1
 	for (int i = 0; i < 16; i++) {
-		const int s = (int) ((mask >> i) & 1u);
-#pragma unroll 1
-		for (int j = 0; j < 4; j++) part[s][F.count[s]][j] = j < 3 ? din[i][j] : 0.f;
-		F.count[s]++;
-	}
-#pragma unroll 1
-	for (int s = 0; s < 2; s++)
-#pragma unroll 1
-		for (int k = 0; k < kMaxEntries; k++) F.idx[s][k] = 0;
-#pragma unroll 1
-	for (int s = 0; s < regions; s++) {
-		float out[kMaxEntries][3];
-		quantise_subset_f(part[s], F.count[s], regions == 2 ? 8 : 16, F.idx[s], out);
-		// GetEndPoints (:1116-1159): ramp points of smallest / largest channel sum
-		float mn = 65504.0f, mx = 0.f;
-		int mini = 0, maxi = 0;
-#pragma unroll 1
-		for (int i = 0; i < F.count[s]; i++) {
-			const float v = out[i][0] + out[i][1] + out[i][2];
-			if (v < mn) { mn = v; mini = i; }
-			if (v > mx) { mx = v; maxi = i; }
+		const bool sub = REGIONS == 2 && ((mask >> i) & 1u);
+		const float v0 = pxc[i], v1 = pxc[16 + i], v2 = pxc[32 + i];
+		float best = 0.f;
+		bool live = true;
+#pragma unroll
+		for (int j = 0; j < NP; j++) {
+			const float p0 = sub ? pal[REGIONS - 1][j][0] : pal[0][j][0], p1 = sub ? pal[REGIONS - 1][j][1] : pal[0][j][1],
+									p2 = sub ? pal[REGIONS - 1][j][2] : pal[0][j][2];
+			const float e = fabsf(v0 - p0) + fabsf(v1 - p1) + fabsf(v2 - p2);
+			if (j == 0) best = e;
+			else if (live) {
+				if (!(best > 0)) live = false;
+				else if (e <= best) best = e;
+				else live = false;
+			}
 		}
-#pragma unroll 1
-		for (int c = 0; c < 3; c++) {
-			float a = out[mini][c], b = out[maxi][c];
+		total += best;
+	}
+	return total;
+}
+
+// FindBestPattern (:904-1037) without ep_shaker_HD. regions 1: all texels; regions 2: `shape`.
+// pxc = channel-major block (3 x 16 floats); io supplies the work arrays.
+template <int REGIONS> H6_HD float fit_shape_t(const float *pxc, int shape, ShapeFit &F, bool is_signed, float *proj, float *dev, int stride) {
+	const uint32_t mask = REGIONS == 2 ? kShape[shape] : 0u;
+	F.idx[0] = F.idx[1] = 0;
+	F.count[0] = F.count[1] = 0;
+#pragma unroll
+	for (int s = 0; s < 2; s++) {
+		if (s < REGIONS) {
+			QuantIOF io;
+			io.px = pxc;
+			io.proj = proj;
+			io.dev = dev;
+			io.stride = stride;
+			int n;
+			io.texels = texels_of_mask(REGIONS == 1 ? 0xffffu : (s ? mask : (~mask & 0xffffu)), n);
+			F.count[s] = n;
+			float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+			F.idx[s] = quantise_points_f(io, n, REGIONS == 2 ? 8 : 16, lo, hi);
 			// clampF16Max (:506-528)
-			const float lo = is_signed ? -31743.f : 0.f;
-			a = a < lo ? lo : (a > 31743.f ? 31743.f : a);
-			b = b < lo ? lo : (b > 31743.f ? 31743.f : b);
-			F.ep[s][0][c] = a;
-			F.ep[s][1][c] = b;
+			const float floor_v = is_signed ? -31743.f : 0.f;
+#pragma unroll
+			for (int c = 0; c < 3; c++) {
+				F.ep[s][0][c] = lo[c] < floor_v ? floor_v : (lo[c] > 31743.f ? 31743.f : lo[c]);
+				F.ep[s][1][c] = hi[c] < floor_v ? floor_v : (hi[c] > 31743.f ? 31743.f : hi[c]);
+			}
+		} else {
+#pragma unroll
+			for (int c = 0; c < 3; c++) F.ep[s][0][c] = F.ep[s][1][c] = 0.f;
 		}
 	}
-	if (regions == 1)
-#pragma unroll 1
-		for (int c = 0; c < 3; c++) F.ep[1][0][c] = F.ep[1][1][c] = 0.f;
-	float pal[2][16][3];
-	build_palette(F.ep, regions, pal);
-	return shape_error(din, pal, regions, mask);
+	return shape_error_direct<REGIONS>(pxc, F.ep, mask);
+}
+H6_HDN float fit_shape(const float *pxc, int regions, int shape, ShapeFit &F, bool is_signed, float *proj, float *dev, int stride) {
+	return regions == 1 ? fit_shape_t<1>(pxc, shape, F, is_signed, proj, dev, stride) : fit_shape_t<2>(pxc, shape, F, is_signed, proj, dev, stride);
 }
 
 // ---- mode fitting (EncodePattern, two-region) ----------------------------------------------------------------
@@ -635,7 +676,7 @@ H6_HDN bool try_mode(const float din[16][4], const ShapeFit &F, int shape, int m
 #pragma unroll 1
 	for (int s = 0; s < 2; s++)
 #pragma unroll 1
-		for (int k = 0; k < kMaxEntries; k++) idx[s][k] = F.idx[s][k];
+		for (int k = 0; k < kMaxEntries; k++) idx[s][k] = (int) ((F.idx[s] >> (4 * k)) & 15u);
 	quantise_endpoints(F.ep, f16, md.nbits, is_signed);
 	swap_indices(f16, idx, F.count, shape);
 	int q[2][2][3];
@@ -743,7 +784,7 @@ H6_HDN void pack_block(const Encoded &E, uint64_t out[2]) {
 }
 
 // texel values as the encoder sees them (:1539-1573): half bit patterns as floats, tiny values flushed
-H6_HD void prepare_block(const float in[64], bool is_signed, float din[16][4]) {
+H6_HD void prepare_block(const float in[64], bool is_signed, float din[16][4], float *pxc) {
 #pragma unroll 1
 	for (int i = 0; i < 16; i++) {
 #pragma unroll 1
@@ -753,6 +794,7 @@ H6_HD void prepare_block(const float in[64], bool is_signed, float din[16][4]) {
 			if ((double) v < 0.00001) o = is_signed ? (float) -(int) float_to_half(fabsf(v / 1.0f)) : 0.0f;
 			else o = (float) float_to_half(v / 1.0f);
 			din[i][c] = o;
+			pxc[c * 16 + i] = o;
 		}
 		din[i][3] = 0.f;
 	}
@@ -772,14 +814,14 @@ H6_HD int pick_mode(const bool *fits, const float *err, const bool *second_fit) 
 
 // CompressBlock (:1521-1652), serial form
 H6_HD void encode_block_serial(const float in[64], bool is_signed, uint64_t out[2]) {
-	float din[16][4];
-	prepare_block(in, is_signed, din);
+	float din[16][4], pxc[48], proj[kMaxEntries], dev[kMaxEntries];
+	prepare_block(in, is_signed, din, pxc);
 	ShapeFit best_fit, cur;
-	float best = fit_shape(din, 1, 0, cur, is_signed); // the one-region error only gates the two-region scan (see header)
+	float best = fit_shape(pxc, 1, 0, cur, is_signed, proj, dev, 1); // the one-region error only gates the two-region scan (see header)
 	int best_shape = -1;
 	if (!(best < FLT_MAX)) best = FLT_MAX;
 	for (int shape = 0; shape < 32; shape++) {
-		const float e = fit_shape(din, 2, shape, cur, is_signed);
+		const float e = fit_shape(pxc, 2, shape, cur, is_signed, proj, dev, 1);
 		if (e < best) {
 			best = e;
 			best_shape = shape;
