@@ -678,6 +678,41 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 	}
 }
 
+// Modes with few independent tasks per block -- mode 6: ONE partition, ONE subset; modes 4 / 5: 16 / 8 (rotation,
+// index selection, vector | scalar) tasks -- leave most lanes of a warp-per-block mapping idle.  For these every
+// THREAD takes a block and runs the serial form of the same search (bc7amd_block.cuh, the code the host build checks
+// against the reference).  Measured at 1024^2 (64 Ki blocks): mode 6 16.7 -> 1.6 ms, mode 4 20.9 -> 14.2 ms, mode 5
+// 10.7 -> 5.0 ms; the partitioned modes 0-3 and 7 are 1.5 .. 6x SLOWER this way and stay warp-per-block.
+__global__ void __launch_bounds__(128) bc7amd_serial_kernel(const AmdParams p, const int mode) {
+	const uint64_t block = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (block >= p.n_blocks) return;
+	const Tables T{p.sp};
+	const uint64_t per_slice = (uint64_t) p.img.blocks_x * p.img.blocks_y;
+	const uint32_t slice = (uint32_t) (block / per_slice);
+	const uint32_t rem = (uint32_t) (block - (uint64_t) slice * per_slice);
+	const uint32_t by = rem / p.img.blocks_x, bx = rem - by * p.img.blocks_x;
+	float in[64];
+#pragma unroll 1
+	for (int i = 0; i < 16; i++) {
+		const float4 t = fetch_rgba(p.img, block, bx, by, slice, i);
+		in[i * 4 + 0] = t.x; in[i * 4 + 1] = t.y; in[i * 4 + 2] = t.z; in[i * 4 + 3] = t.w;
+	}
+	BlockInput B;
+	prepare_block(in, p.mode_mask, B);
+	const real carried = p.first ? A7_HUGE : p.best_err[block];
+	real best = carried;
+	uint64_t out[2] = {0, 0};
+	if (B.mode_mask & p.launch_modes & (1u << mode)) {
+		uint64_t tmp[2];
+		const real e = (mode_info(mode).alpha != 2) ? compress_single_index<true>(T, B, mode, tmp) : compress_dual_index<true>(T, B, mode, tmp);
+		if (e < best) { best = e; out[0] = tmp[0]; out[1] = tmp[1]; }
+	}
+	if (p.first || best < carried) {
+		p.dst[block] = make_uint4((uint32_t) out[0], (uint32_t) (out[0] >> 32), (uint32_t) out[1], (uint32_t) (out[1] >> 32));
+		p.best_err[block] = best;
+	}
+}
+
 } // namespace
 
 cudaError_t init_bc7amd_tables() {
@@ -746,6 +781,7 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 									img.format == B200IC_FMT_BLOCKS_RGBA8;
 	static const int variant = getenv("B200IC_AMD_VARIANT") ? atoi(getenv("B200IC_AMD_VARIANT")) : 3;
 	static const int fused = getenv("B200IC_AMD_FUSED") ? atoi(getenv("B200IC_AMD_FUSED")) : 0;
+	static const int serial_mask = getenv("B200IC_AMD_SERIAL") ? (int) strtol(getenv("B200IC_AMD_SERIAL"), nullptr, 0) : 0x70;
 	// One launch per mode, in the reference's visiting order {6,4,3,1,2,0,7,5} (src/amd_bc7_body.cpp:1400), the running
 	// best block and its error carried in dst / best_err: every SM then runs ONE mode's code at a time.  The fused
 	// all-modes launch is 13 % (opaque) to 26 % (translucent) slower than the sum of its single-mode launches
@@ -764,7 +800,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 			p.launch_modes = 1u << mode;
 		}
 		p.first = launches == 0;
-		if (u8 && variant == 4) bc7amd_kernel<true, 4><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
+		if (u8 && !fused && ((serial_mask >> mode) & 1)) bc7amd_serial_kernel<<<(unsigned) ((p.n_blocks + 127) / 128), 128, 0, stream>>>(p, mode);
+		else if (u8 && variant == 4) bc7amd_kernel<true, 4><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
 		else if (u8 && variant == 2) bc7amd_kernel<true, 2><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
 		else if (u8) bc7amd_kernel<true, 3><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
 		else bc7amd_kernel<false, 4><<<(unsigned) grid, kWarps * 32, smem, stream>>>(p);
