@@ -159,8 +159,9 @@ def cpu_reference_sample(codec: int, size: int, seed: int, budget_s: float, step
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        ref.encode(REF_CODEC[codec], img, wl["fmt"], threads=threads)
+        ref_blocks = ref.encode(REF_CODEC[codec], img, wl["fmt"], threads=threads)
         times.append(time.perf_counter() - t0)
+    cpu_reference_sample.last = (idx, ref_blocks, img)
     dt = sum(times) / len(times)
     mpix = n_rows * 4 * size / dt / 1e6
     return mpix, {"value": mpix, "unit": "Mpix/s", "cores": threads, "kind": "reference",
@@ -258,6 +259,32 @@ def bench_batch(args, codec, cname, rank, local_rank, world):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _parity(codec, size, gpu_blocks, bb):
+    """The block-rows the CPU reference just encoded for cpu_baseline, compared with the SAME rows of the GPU result of
+    the timed workload (rank 0's image): identical-block fraction and, for BC7 / BC1, decoded PSNR of both."""
+    last = getattr(cpu_reference_sample, "last", None)
+    if last is None:
+        return None
+    idx, ref_blocks, img = last
+    bx = size // 4
+    g = gpu_blocks.reshape(size // 4, bx, bb)[idx].reshape(-1, bb)
+    same = float((g == ref_blocks).all(axis=1).mean())
+    out = {"rows": len(idx), "blocks": int(len(ref_blocks)), "identical_fraction": same}
+    try:
+        from oracle import metrics
+        if codec in (7, 8):
+            out["psnr_gpu_db"] = metrics.psnr_bc7(g, img)
+            out["psnr_reference_db"] = metrics.psnr_bc7(ref_blocks, img)
+        elif codec == 1:
+            out["psnr_gpu_db"] = metrics.psnr_bc1(g, img)
+            out["psnr_reference_db"] = metrics.psnr_bc1(ref_blocks, img)
+        if "psnr_gpu_db" in out:
+            out["delta_psnr_db"] = out["psnr_gpu_db"] - out["psnr_reference_db"]
+    except Exception as e:  # the decoders are test infrastructure; parity by bytes stands without them
+        out["psnr_error"] = repr(e)
+    return out
 
 
 def main():
@@ -415,6 +442,7 @@ def main():
         if not args.no_cpu and world == 1:
             _, info = cpu_reference_sample(codec, size, 3, args.cpu_budget, 1)
             out["cpu_baseline"] = info
+            out["parity"] = _parity(codec, size, d_dst.cpu().numpy(), bb)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
