@@ -294,8 +294,11 @@ int b200ic_encode_host(int codec, const void *h_src, int format, uint32_t width,
 
 	const uint64_t pitch = row_pitch_bytes ? row_pitch_bytes : (uint64_t) width * tb;
 	const uint32_t blocks_x = (width + 3) / 4, blocks_y = (height + 3) / 4;
-	// chunk = whole block-rows, ~16 MiB of input each so copies overlap the kernels of neighbouring chunks
-	uint32_t rows_per_chunk = (uint32_t) ((16ull << 20) / (pitch * 4));
+	// chunk = whole block-rows, ~16 MiB of input each so copies overlap the kernels of neighbouring chunks.  AMD BC7
+	// spends seconds per 256 MiB (the copies are noise) and runs one launch per mode: big chunks keep launches of
+	// DIFFERENT modes from sharing the SMs (they evict each other's code, see launch_bc7amd)
+	const uint64_t chunk_bytes = codec == B200IC_BC7_AMD ? (256ull << 20) : (16ull << 20);
+	uint32_t rows_per_chunk = (uint32_t) (chunk_bytes / (pitch * 4));
 	if (rows_per_chunk < 1) rows_per_chunk = 1;
 	if (rows_per_chunk > blocks_y) rows_per_chunk = blocks_y;
 	const uint32_t chunks_per_slice = (blocks_y + rows_per_chunk - 1) / rows_per_chunk;

@@ -245,18 +245,19 @@ H6_HDN uint64_t lattice_quantise_f(const QuantIOF &io, int k, int n) {
 		dm /= (float) n;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) io.dev[i * st] -= dm;
-		uint64_t ord = 0; // stable rank of every deviation (comparator a - b > 0)
+		// stable rank of every deviation (what an insertion sort with the comparator `a - b > 0` produces), one compare
+		// per PAIR: for i < j exactly one of the two gains a rank -- entry i if d_i > d_j, else entry j (a - b > 0 is
+		// a > b for these finite values: a difference of distinct finite numbers never rounds to zero)
+		uint64_t rank4 = 0;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			const float ki = io.dev[i * st];
-			int rank = 0;
 #pragma unroll 1
-			for (int j = 0; j < n; j++) {
-				const float kj = io.dev[j * st];
-				rank += ((ki - kj > 0) || (!(kj - ki > 0) && j < i)) ? 1 : 0;
-			}
-			ord |= (uint64_t) i << (4 * rank);
+			for (int j = i + 1; j < n; j++) rank4 += 1ull << (4 * (ki > io.dev[j * st] ? i : j));
 		}
+		uint64_t ord = 0;
+#pragma unroll 1
+		for (int i = 0; i < n; i++) ord |= (uint64_t) i << (4 * (int) ((rank4 >> (4 * i)) & 15u));
 		float mm = 0, l = 0;
 		int j = -1;
 #pragma unroll 1

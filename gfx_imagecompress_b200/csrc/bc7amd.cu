@@ -413,7 +413,36 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 		ws.in[lane * 4 + 0] = t.x; ws.in[lane * 4 + 1] = t.y; ws.in[lane * 4 + 2] = t.z; ws.in[lane * 4 + 3] = t.w;
 	}
 	__syncwarp();
-	if (lane == 0) prepare_block(ws.in, p.mode_mask, ws.B);
+	{ // prepare_block (bc7amd_core.cuh) with one texel per lane
+		bool na = false, zo = false;
+		real v[4] = {0, 0, 0, 0};
+		if (lane < 16) {
+			const float a = ws.in[lane * 4 + 3];
+			if (a < 1.0) na = true;
+			else if (((double) a >= 0.99999) || ((double) a < 0.00001)) zo = true;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				v[j] = (real) (ws.in[lane * 4 + j] * 255.0f);
+				ws.B.px[lane][j] = v[j];
+				ws.B.pxc[j][lane] = v[j];
+			}
+		}
+		const bool needs_alpha = __any_sync(FULL, na), zero_one = __any_sync(FULL, zo);
+		real range = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			real mn = lane < 16 ? v[j] : A7_HUGE, mx = lane < 16 ? v[j] : 0;
+			mx = mx > 0 ? mx : 0; // the reference's running maximum starts at 0
+			for (int d = 8; d > 0; d >>= 1) {
+				const real mn2 = __shfl_xor_sync(FULL, mn, d), mx2 = __shfl_xor_sync(FULL, mx, d);
+				mn = mn2 < mn ? mn2 : mn;
+				mx = mx2 > mx ? mx2 : mx;
+			}
+			const real r = mx - mn;
+			range = j == 0 ? r : (range > r ? range : r);
+		}
+		if (lane == 0) ws.B.mode_mask = filter_modes(p.mode_mask, needs_alpha, zero_one, range < 1e-10);
+	}
 	__syncwarp();
 	const uint32_t mask = ws.B.mode_mask & p.launch_modes;
 	if (mask == 0 && !p.first) return; // whole warp

@@ -290,18 +290,19 @@ A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
 #pragma unroll 1
 		for (int i = 0; i < n; i++) io.dev[i * st] -= dm;
 		// stable rank of every deviation (what an insertion sort with the comparator `a - b > 0` produces)
-		uint64_t ord = 0;
+		// stable rank of every deviation (what an insertion sort with the comparator `a - b > 0` produces), one compare
+		// per PAIR: for i < j exactly one of the two gains a rank -- entry i if d_i > d_j, else entry j (a - b > 0 is
+		// a > b for these finite values: a difference of distinct finite numbers never rounds to zero)
+		uint64_t rank4 = 0;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			const real ki = io.dev[i * st];
-			int rank = 0;
 #pragma unroll 1
-			for (int j = 0; j < n; j++) {
-				const real kj = io.dev[j * st];
-				rank += ((ki - kj > 0) || (!(kj - ki > 0) && j < i)) ? 1 : 0;
-			}
-			ord |= (uint64_t) i << (4 * rank);
+			for (int j = i + 1; j < n; j++) rank4 += 1ull << (4 * (ki > io.dev[j * st] ? i : j));
 		}
+		uint64_t ord = 0;
+#pragma unroll 1
+		for (int i = 0; i < n; i++) ord |= (uint64_t) i << (4 * (int) ((rank4 >> (4 * i)) & 15u));
 		real mm = 0, l = 0;
 		int j = -1;
 #pragma unroll 1
@@ -1155,6 +1156,20 @@ struct BlockInput {
 	uint32_t mode_mask; // after the filter of :1340-1380
 };
 
+// the mode filter of CompressBlock (:1340-1380)
+A7_HD uint32_t filter_modes(uint32_t valid_mode_mask, bool needs_alpha, bool zero_one, bool solid) {
+	uint32_t mask = valid_mode_mask ? valid_mode_mask : 0xCFu;
+#pragma unroll 1
+	for (int m = 0; m < 8; m++) {
+		if (!(mask & (1u << m))) continue;
+		const int at = mode_info(m).alpha;
+		if (needs_alpha && at == 0) mask &= ~(1u << m);
+		if (!solid && !needs_alpha && at == 1) mask &= ~(1u << m);
+		if (needs_alpha && zero_one && at == 1) mask &= ~(1u << m);
+	}
+	return mask;
+}
+
 // CompressBlock's set-up (:1296-1380): scale to 0..255, alpha classification, mode filter
 A7_HDN void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInput &B) {
 	bool needs_alpha = false, zero_one = false;
@@ -1176,17 +1191,7 @@ A7_HDN void prepare_block(const float in[64], uint32_t valid_mode_mask, BlockInp
 	real range = mx[0] - mn[0];
 #pragma unroll 1
 	for (int j = 1; j < 4; j++) range = range > (mx[j] - mn[j]) ? range : (mx[j] - mn[j]);
-	const bool solid = range < 1e-10;
-	uint32_t mask = valid_mode_mask ? valid_mode_mask : 0xCFu;
-#pragma unroll 1
-	for (int m = 0; m < 8; m++) {
-		if (!(mask & (1u << m))) continue;
-		const int at = mode_info(m).alpha;
-		if (needs_alpha && at == 0) mask &= ~(1u << m);
-		if (!solid && !needs_alpha && at == 1) mask &= ~(1u << m);
-		if (needs_alpha && zero_one && at == 1) mask &= ~(1u << m);
-	}
-	B.mode_mask = mask;
+	B.mode_mask = filter_modes(valid_mode_mask, needs_alpha, zero_one, range < 1e-10);
 }
 
 A7_HD void gather_subset(const BlockInput &B, int subsets, int partition, int subset, int dim, real out[][4], int &n) {
