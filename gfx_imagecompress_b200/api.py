@@ -169,7 +169,7 @@ class _HostProgress:
 
 
 def encode_device(codec: int, src, fmt: int, width: int, height: int, slices: int = 1, opts: Opts | None = None,
-                  out=None, stream=None):
+                  out=None, stream=None, row_pitch: int = 0, slice_pitch: int = 0):
     """Device-resident encode through b200ic_encode_device. `src` / `out` are CUDA torch tensors (plumbing only:
     torch provides the memory and the stream). Asynchronous on torch's current stream unless `stream` is given."""
     import torch
@@ -180,7 +180,7 @@ def encode_device(codec: int, src, fmt: int, width: int, height: int, slices: in
         out = torch.empty((nb, BLOCK_BYTES[codec]), dtype=torch.uint8, device=src.device)
     st = stream if stream is not None else torch.cuda.current_stream(src.device).cuda_stream
     with torch.cuda.device(src.device):
-        rc = L.b200ic_encode_device(codec, src.data_ptr(), fmt, width, height, 0, 0, slices,
+        rc = L.b200ic_encode_device(codec, src.data_ptr(), fmt, width, height, row_pitch, slice_pitch, slices,
                                     C.byref(opts) if opts is not None else None, out.data_ptr(), st)
     _check(rc, "b200ic_encode_device")
     return out
