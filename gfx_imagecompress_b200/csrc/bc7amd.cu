@@ -98,6 +98,8 @@ struct AmdParams {
 	real *best_err;        // per block: error of the block currently in dst (carried from launch to launch)
 	int first;             // first launch of the sequence: nothing to compare with
 	int zsplit_single, zsplit_dual; // experiment knobs: 0 = auto / built-in choice
+	int split_n;                    // cube items of subsets with >= split_n texels are shared by two lanes (0 = never)
+	int prune;                      // 1: per-lane exact branch-and-bound in the cube walk (measured slower than the exhaustive walk)
 };
 
 __device__ __forceinline__ uint64_t pack_idx(const int *idx, int n) {
@@ -141,7 +143,7 @@ __device__ __noinline__ void cube_begin_pass(const Tables &T, CubeTask &t, uint6
 }
 
 // ep_shaker_d for all tasks of the warp (u8 path). On return task[i].err_o / best_idx hold its result.
-__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit_in, unsigned lane) {
+__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit_in, unsigned lane, bool prune, int split_n) {
 	int zsplit = zsplit_in > 0 ? zsplit_in : 1;
 	if ((int) lane < ntasks) {
 		CubeTask &t = ws.task[lane];
@@ -153,21 +155,25 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 	__syncwarp();
 	for (int pass = 0; pass < 2; pass++) {
 		// ---- lay the items out: tasks sorted by (clog, n) descending so that the lanes of a round agree on trip counts
-		int count = 0, sortkey = -1;
+		int count = 0, sortkey = -1, split = 1;
 		if ((int) lane < ntasks && !ws.task[lane].done) {
 			const CubeTask &t = ws.task[lane];
 			count = qp_count(t.Mi, (1 << t.clog) - 1);
 			sortkey = t.clog * 32 + t.n;
+			split = (split_n > 0 && t.n >= split_n) ? 2 : 1;
 		}
 		if (zsplit_in <= 0) {
 			// cut every item into z-slices of the endpoint cube so that the rounds of 32 lanes are as full as possible:
 			// cost(z) = rounds(z) * (4 / z) quarter-cubes; ties go to the coarser split (the endpoint fit is per item)
-			int tot1 = count;
+			int tot1 = count * split;
 			for (int dlt = 16; dlt > 0; dlt >>= 1) tot1 += __shfl_xor_sync(FULL, tot1, dlt);
 			const int c1 = ((tot1 + 31) >> 5) * 4, c2 = ((2 * tot1 + 31) >> 5) * 2, c4 = (4 * tot1 + 31) >> 5;
 			zsplit = c4 < c2 ? (c4 < c1 ? 4 : 1) : (c2 < c1 ? 2 : 1);
 		}
-		count *= zsplit;
+		// an item of a big subset is shared by two ADJACENT lanes, each summing half of the texels: the tasks are laid out
+		// by descending size, so the split ones come first and every pair starts on an even item (batches and rounds
+		// are even too)
+		count *= zsplit * split;
 		int rank = 0;
 		for (int o = 0; o < ntasks; o++) {
 			const int ok = __shfl_sync(FULL, sortkey, o);
@@ -201,15 +207,18 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 				}
 				const CubeTask &t = ws.task[ti];
 				const int local = it - t.item_base;
-				const int qp = local / zsplit, zp = local - qp * zsplit;
+				const int hs = (split_n > 0 && t.n >= split_n) ? 2 : 1;
+				const int qp = local / (zsplit * hs), rest = local - qp * (zsplit * hs);
+				const int zp = rest / hs, half = hs == 2 ? rest - zp * hs : -1;
 				int q, p;
 				qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
 				const int bits[3] = {t.bits, t.bits, t.bits};
 				const int zn = 4 / zsplit;
 				uint32_t key;
 				uint64_t idx;
-				if (t.clog == 2) cube_item_u8<2>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx);
-				else cube_item_u8<3>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx);
+				const unsigned pm = split_n > 0 ? __activemask() : 0u;
+				if (t.clog == 2) cube_item_u8<2>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx, prune, half, pm);
+				else cube_item_u8<3>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx, prune, half, pm);
 				ws.item_key[it - b0] = ((uint64_t) (key >> 8) << 16) | ((uint64_t) qp << 8) | (uint64_t) (key & 255u);
 				ws.item_idx[it - b0] = idx;
 			}
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 			if (U8) {
 				// shake_subset (:709-805): ep_shaker_d, ep_shaker_2_d on the quantiser's indices, and where the former
 				// won, ep_shaker_2_d again on its indices
-				if (cube_u8) cube_phase(T, ws, ntasks, p.zsplit_single ? p.zsplit_single : (subsets == 3 ? 1 : 0), lane); // 3 subsets: small n, the per-item endpoint fit outweighs fuller rounds (measured)
+				if (cube_u8) cube_phase(T, ws, ntasks, p.zsplit_single ? p.zsplit_single : (subsets == 3 ? 1 : 0), lane, p.prune != 0, p.split_n); // 3 subsets: small n, the per-item endpoint fit outweighs fuller rounds (measured)
 				window_phase(T, ws, ntasks, lane);
 				if (cube_u8) {
 					if ((int) lane < ntasks) {
@@ -637,7 +646,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 			}
 			__syncwarp();
 			if (U8) {
-				cube_phase(T, ws, ntasks, p.zsplit_dual ? p.zsplit_dual : (ntasks <= 8 ? 4 : 2), lane);
+				cube_phase(T, ws, ntasks, p.zsplit_dual ? p.zsplit_dual : (ntasks <= 8 ? 4 : 2), lane, p.prune != 0, 0);
 				if ((int) lane < ntasks) {
 					CubeTask &t = ws.task[lane];
 					t.w_index = t.best_idx;
@@ -801,6 +810,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	p.mode_mask = (uint32_t) opts.amd_mode_mask & 0xffu;
 	p.zsplit_single = getenv("B200IC_AMD_ZS") ? atoi(getenv("B200IC_AMD_ZS")) : 0;
 	p.zsplit_dual = getenv("B200IC_AMD_ZD") ? atoi(getenv("B200IC_AMD_ZD")) : 0;
+	p.split_n = getenv("B200IC_AMD_SPLITN") ? atoi(getenv("B200IC_AMD_SPLITN")) : 0; // measured: 8 / 6 are 3-4 % slower than no split
+	p.prune = getenv("B200IC_AMD_PRUNE") ? atoi(getenv("B200IC_AMD_PRUNE")) : 0;
 	if (p.n_blocks == 0) return cudaSuccess;
 	const uint64_t grid = (p.n_blocks + kWarps - 1) / kWarps;
 	const size_t smem = kWarps * sizeof(WarpScratch);

@@ -176,10 +176,17 @@ A7_HD int gray_position(int s) { // p1 with gray(p1) == s, 6 bits
 
 // All lattices of ep_shaker_d for one (q, p): returns min over (lattice, corner) of err << 8 | lattice << 6 | gray position,
 // and that corner's index assignment (4 bits per texel).
+// i0..i1 = the texels this caller sums over.  On the GPU an item with many texels is shared by two adjacent lanes
+// (halves of its texel list): `pair_mask` != 0 names the lanes that meet at the exchange after every corner, `paired`
+// says whether this lane's partner (lane ^ 1) holds the other half; the two then see the same keys and keep the index
+// nibbles of their own texels (merged by the caller).
 template <int CLOG>
 A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real epa[2][4], int use_par, int bcc, int z0, int z1, uint32_t &best_key,
-													 uint64_t &best_idx) {
+													 uint64_t &best_idx, int i0 = 0, int i1 = -1, unsigned pair_mask = 0, bool paired = false) {
 	constexpr int C = 1 << CLOG;
+	if (i1 < 0) i1 = n;
+	(void) pair_mask;
+	(void) paired;
 	// floor of each ideal endpoint on the parity-0 and parity-1 lattice
 	int fl[2][3][2];
 #pragma unroll 1
@@ -222,7 +229,7 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 						uint32_t err = 0;
 						uint64_t idx = 0;
 #pragma unroll 1
-						for (int i = 0; i < n; i++) {
+						for (int i = i0; i < i1; i++) {
 							const uint32_t di = d[i];
 							uint32_t m = 0xffffffffu;
 #pragma unroll
@@ -230,6 +237,12 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 							err += m >> 4;
 							idx |= (uint64_t) (m & 15u) << (4 * i);
 						}
+#if defined(__CUDA_ARCH__)
+						if (pair_mask) {
+							const uint32_t other = __shfl_xor_sync(pair_mask, err, 1);
+							if (paired) err += other;
+						}
+#endif
 						const uint32_t key = (err << 8) | ((uint32_t) lattice << 6) | (uint32_t) gray_position(x | (y << 2) | (z << 4));
 						if (key < best_key) { best_key = key; best_idx = idx; }
 					}
@@ -465,15 +478,27 @@ A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
 // lattice. key = err << 8 | lattice << 6 | gray position (minimum = first strict minimum in the reference's order).
 template <int CLOG>
 A7_HDN void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, const int *bits, int type, int z0, int z1, uint32_t &key,
-												uint64_t &idx, bool prune = true) {
+												uint64_t &idx, bool prune = false, int half = -1, unsigned pair_mask = 0) {
 	ClusterAcc<CLOG> cs;
 	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
 	real epa[2][4];
 	fit_endpoints_acc<CLOG>(cs, 3, epa);
 	key = 0xffffffffu;
 	idx = 0;
-	if (prune) cube_search_pruned_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
-	else cube_search_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
+	if (prune) {
+		cube_search_pruned_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx);
+		return;
+	}
+	// half = -1: all texels; 0 / 1: the first ceil(n / 2) texels / the rest, the partner lane holding the other half
+	const int mid = (n + 1) >> 1;
+	const int i0 = half == 1 ? mid : 0, i1 = half == 0 ? mid : n;
+	cube_search_u8<CLOG>(d, n, bits, epa, (type == BCC || type == SAME_PAR), (type == BCC), z0, z1, key, idx, i0, i1, pair_mask, half >= 0);
+#if defined(__CUDA_ARCH__)
+	if (pair_mask) {
+		const uint32_t lo = __shfl_xor_sync(pair_mask, (uint32_t) idx, 1), hi = __shfl_xor_sync(pair_mask, (uint32_t) (idx >> 32), 1);
+		if (half >= 0) idx |= (uint64_t) lo | ((uint64_t) hi << 32);
+	}
+#endif
 }
 
 // ep_shaker_d on packed 8-bit data (dimension 3). index_io in/out; returns the SSE (exact integer as real).
