@@ -195,6 +195,13 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 		for (int k = 0; k < 3; k++)
 #pragma unroll 1
 			for (int par = 0; par <= use_par; par++) fl[e][k][par] = endpoint_floor(epa[e][k], bits[k], use_par, par);
+	// The walk only needs every corner's ERROR (3 instructions per texel and ramp entry: |palette - texel| per byte,
+	// sum of squares, running minimum); the index vector is wanted for the winning corner alone, whose palette is kept
+	// and re-scanned once at the end with the (distance << 4 | entry) keys that make the lowest entry win ties.
+	uint32_t win_pal[C];
+#pragma unroll
+	for (int c = 0; c < C; c++) win_pal[c] = 0;
+	bool improved = false;
 	int lattice = 0;
 #pragma unroll 1
 	for (int odd = 0; odd <= use_par; odd++)
@@ -227,15 +234,13 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 #pragma unroll
 						for (int c = 0; c < C; c++) pal[c] = pzy[c] | byte_of(tab[0][x], c);
 						uint32_t err = 0;
-						uint64_t idx = 0;
 #pragma unroll 1
 						for (int i = i0; i < i1; i++) {
 							const uint32_t di = d[i];
 							uint32_t m = 0xffffffffu;
 #pragma unroll
-							for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], di) << 4) | (uint32_t) c);
-							err += m >> 4;
-							idx |= (uint64_t) (m & 15u) << (4 * i);
+							for (int c = 0; c < C; c++) m = umin32(m, sq_dist4(pal[c], di));
+							err += m;
 						}
 #if defined(__CUDA_ARCH__)
 						if (pair_mask) {
@@ -244,10 +249,27 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 						}
 #endif
 						const uint32_t key = (err << 8) | ((uint32_t) lattice << 6) | (uint32_t) gray_position(x | (y << 2) | (z << 4));
-						if (key < best_key) { best_key = key; best_idx = idx; }
+						if (key < best_key) {
+							best_key = key;
+							improved = true;
+#pragma unroll
+							for (int c = 0; c < C; c++) win_pal[c] = pal[c];
+						}
 					}
 				}
 		}
+	if (improved) {
+		uint64_t idx = 0;
+#pragma unroll 1
+		for (int i = i0; i < i1; i++) {
+			const uint32_t di = d[i];
+			uint32_t m = 0xffffffffu;
+#pragma unroll
+			for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(win_pal[c], di) << 4) | (uint32_t) c);
+			idx |= (uint64_t) (m & 15u) << (4 * i);
+		}
+		best_idx = idx;
+	}
 }
 
 // The same search as cube_search_u8 with an exact branch-and-bound.  For a corner (x, y, z) of a lattice the error is
