@@ -283,13 +283,31 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 #define A7_STATS_CORNERS(evaluated, total)
 #endif
 template <int CLOG>
-A7_HD void cube_corner_u8(const uint32_t *d, int n, const uint64_t tab[3][4], int x, int y, int z, int lattice, uint32_t &best_key, uint64_t &best_idx) {
+A7_HD void cube_corner_u8(const uint32_t *d, int n, const uint64_t tab[3][4], int x, int y, int z, int lattice, uint32_t &best_key, uint32_t *win_pal) {
 	constexpr int C = 1 << CLOG;
 	uint32_t pal[C];
 	const uint64_t t0 = tab[0][x], t1 = tab[1][y], t2 = tab[2][z];
 #pragma unroll
 	for (int c = 0; c < C; c++) pal[c] = byte_of(t0, c) | (byte_of(t1, c) << 8) | (byte_of(t2, c) << 16);
 	uint32_t err = 0;
+#pragma unroll 1
+	for (int i = 0; i < n; i++) {
+		const uint32_t di = d[i];
+		uint32_t m = 0xffffffffu;
+#pragma unroll
+		for (int c = 0; c < C; c++) m = umin32(m, sq_dist4(pal[c], di));
+		err += m;
+	}
+	const uint32_t key = (err << 8) | ((uint32_t) lattice << 6) | (uint32_t) gray_position(x | (y << 2) | (z << 4));
+	if (key < best_key) {
+		best_key = key;
+#pragma unroll
+		for (int c = 0; c < C; c++) win_pal[c] = pal[c];
+	}
+}
+// index vector of the texels against a palette: the lowest entry wins ties (keys distance << 4 | entry)
+template <int CLOG> A7_HD uint64_t palette_indices_u8(const uint32_t *d, int n, const uint32_t *pal) {
+	constexpr int C = 1 << CLOG;
 	uint64_t idx = 0;
 #pragma unroll 1
 	for (int i = 0; i < n; i++) {
@@ -297,11 +315,9 @@ A7_HD void cube_corner_u8(const uint32_t *d, int n, const uint64_t tab[3][4], in
 		uint32_t m = 0xffffffffu;
 #pragma unroll
 		for (int c = 0; c < C; c++) m = umin32(m, (sq_dist4(pal[c], di) << 4) | (uint32_t) c);
-		err += m >> 4;
 		idx |= (uint64_t) (m & 15u) << (4 * i);
 	}
-	const uint32_t key = (err << 8) | ((uint32_t) lattice << 6) | (uint32_t) gray_position(x | (y << 2) | (z << 4));
-	if (key < best_key) { best_key = key; best_idx = idx; }
+	return idx;
 }
 template <int CLOG>
 A7_HD void cube_search_pruned_u8(const uint32_t *d, int n, const int *bits, const real epa[2][4], int use_par, int bcc, int z0, int z1,
@@ -314,6 +330,10 @@ A7_HD void cube_search_pruned_u8(const uint32_t *d, int n, const int *bits, cons
 		for (int k = 0; k < 3; k++)
 #pragma unroll 1
 			for (int par = 0; par <= use_par; par++) fl[e][k][par] = endpoint_floor(epa[e][k], bits[k], use_par, par);
+	uint32_t win_pal[C];
+#pragma unroll
+	for (int c = 0; c < C; c++) win_pal[c] = 0;
+	const uint32_t key_in = best_key;
 	int lattice = 0;
 #pragma unroll 1
 	for (int odd = 0; odd <= use_par; odd++)
@@ -363,7 +383,7 @@ A7_HD void cube_search_pruned_u8(const uint32_t *d, int n, const int *bits, cons
 				if (lb[2][z] < lb[2][sz]) sz = z;
 			int evaluated = 0;
 			if (lb[0][sx] + lb[1][sy] + lb[2][sz] <= (best_key >> 8)) {
-				cube_corner_u8<CLOG>(d, n, tab, sx, sy, sz, lattice, best_key, best_idx);
+				cube_corner_u8<CLOG>(d, n, tab, sx, sy, sz, lattice, best_key, win_pal);
 				evaluated++;
 			}
 			uint64_t mask = 0;
@@ -386,12 +406,13 @@ A7_HD void cube_search_pruned_u8(const uint32_t *d, int n, const int *bits, cons
 				mask &= mask - 1;
 				const int x = cnr & 3, y = (cnr >> 2) & 3, z = cnr >> 4;
 				if (lb[0][x] + lb[1][y] + lb[2][z] <= (best_key >> 8)) {
-					cube_corner_u8<CLOG>(d, n, tab, x, y, z, lattice, best_key, best_idx);
+					cube_corner_u8<CLOG>(d, n, tab, x, y, z, lattice, best_key, win_pal);
 					evaluated++;
 				}
 			}
 			A7_STATS_CORNERS(evaluated, 16 * (z1 - z0));
 		}
+	if (best_key != key_in) best_idx = palette_indices_u8<CLOG>(d, n, win_pal);
 }
 
 // Building blocks of the two-phase form of the pruned search used by the CUDA kernel (bc7amd.cu, cube_batch): phase A
