@@ -58,6 +58,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
                 os.path.join(ROOT, "include", "gfx_imagecompress", "imagecompress.h"), os.path.abspath(__file__)]
     present = [(s, f) for s, f in UNITS if os.path.exists(os.path.join(CSRC, s))]
     defines = ["-D" + HAVE[s] for s, _ in present if s in HAVE]
+    defines += ["-D" + d for d in os.environ.get("B200IC_EXTRA_DEFS", "").split() if d]  # e.g. B200IC_AMD_TIMING (debug builds)
     cc = nvcc()
     jobs = []
     objs = []

@@ -42,6 +42,28 @@ __device__ __forceinline__ const uint8_t *quantise_order(int subsets, int nparts
 	return subsets == 3 ? (nparts == 16 ? c_qorder : c_qorder + 48) : c_qorder + 240;
 }
 
+// Optional phase timing (build with -DB200IC_AMD_TIMING, read with b200ic_amd_timing): clock64 deltas of lane 0 summed
+// per phase over all warps. Slots: 0 quantise, 1 rank+task setup, 2 cube, 3 window, 4 window (2nd), 5 pick+pack,
+// 6 cube items evaluated, 7 cube rounds of 32 lanes, 8 window items, 9 window rounds, 10 cube passes
+#ifdef B200IC_AMD_TIMING
+__device__ unsigned long long g_amd_timing[16];
+#define AMD_T0() long long t__ = clock64()
+#define AMD_T(slot)                                                         \
+	do {                                                                      \
+		const long long n__ = clock64();                                        \
+		if (lane == 0) atomicAdd(&g_amd_timing[slot], (unsigned long long) (n__ - t__)); \
+		t__ = n__;                                                              \
+	} while (0)
+#define AMD_COUNT(slot, v)                                                  \
+	do {                                                                      \
+		if (lane == 0) atomicAdd(&g_amd_timing[slot], (unsigned long long) (v)); \
+	} while (0)
+#else
+#define AMD_T0()
+#define AMD_T(slot)
+#define AMD_COUNT(slot, v)
+#endif
+
 struct ShakeOut {
 	real err;
 	uint64_t idx; // 4 bits per subset-local entry
@@ -196,6 +218,9 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 		}
 		__syncwarp();
 		if (total == 0) break;
+		AMD_COUNT(6, total);
+		AMD_COUNT(7, (total + 31) / 32);
+		AMD_COUNT(10, 1);
 		for (int b0 = 0; b0 < total; b0 += kItemBatch) {
 			const int b1 = min(total, b0 + kItemBatch);
 			for (int it = b0 + (int) lane; it < b1; it += 32) {
@@ -346,6 +371,8 @@ __device__ __noinline__ void window_phase(const Tables &T, WarpScratch &ws, int 
 		}
 		const int total = layout_items(ws, ntasks, count, sortkey, lane);
 		if (total == 0) break;
+		AMD_COUNT(8, total);
+		AMD_COUNT(9, (total + 31) / 32);
 		for (int b0 = 0; b0 < total; b0 += kItemBatch) {
 			const int b1 = min(total, b0 + kItemBatch);
 			for (int it = b0 + (int) lane; it < b1; it += 32) {
@@ -467,6 +494,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 			const ShakeParams sp = single_index_shake_params(mode);
 			const int nparts = 1 << mi.partition_bits, subsets = mi.subsets;
 			const uint8_t *qorder = subsets > 1 ? quantise_order(subsets, nparts) : nullptr;
+			AMD_T0();
 			QuantIO io;
 			io.px = &ws.B.pxc[0][0];
 			io.chan = 0xE4u;
@@ -485,6 +513,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 				ws.qidx[part][s] = packed;
 			}
 			__syncwarp();
+			AMD_T(0);
 			for (int part = (int) lane; part < nparts; part += 32) {
 				real e = 0;
 				for (int s = 0; s < subsets; s++) e += ws.serr[part][s];
@@ -533,8 +562,11 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 			if (U8) {
 				// shake_subset (:709-805): ep_shaker_d, ep_shaker_2_d on the quantiser's indices, and where the former
 				// won, ep_shaker_2_d again on its indices
+				AMD_T(1);
 				if (cube_u8) cube_phase(T, ws, ntasks, p.zsplit_single ? p.zsplit_single : (subsets == 3 ? 1 : 0), lane, p.prune != 0, p.split_n); // 3 subsets: small n, the per-item endpoint fit outweighs fuller rounds (measured)
+				AMD_T(2);
 				window_phase(T, ws, ntasks, lane);
+				AMD_T(3);
 				if (cube_u8) {
 					if ((int) lane < ntasks) {
 						CubeTask &t = ws.task[lane];
@@ -543,6 +575,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 					}
 					__syncwarp();
 					window_phase(T, ws, ntasks, lane);
+					AMD_T(4);
 				}
 			}
 			if ((int) lane < ntasks) {
@@ -587,6 +620,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 				ws.blk_err = be;
 			}
 			__syncwarp();
+			AMD_T(5);
 		} else {
 			const int nrot = 1 << mi.rotation_bits, nsel = 1 << mi.index_mode_bits;
 			const int combos = nrot * nsel;
@@ -752,6 +786,18 @@ __global__ void __launch_bounds__(128) bc7amd_serial_kernel(const AmdParams p, c
 }
 
 } // namespace
+
+#ifdef B200IC_AMD_TIMING
+extern "C" __attribute__((visibility("default"))) int b200ic_amd_timing(unsigned long long *out, int reset) {
+	cudaDeviceSynchronize();
+	if (out) cudaMemcpyFromSymbol(out, g_amd_timing, sizeof(g_amd_timing));
+	if (reset) {
+		unsigned long long z[16] = {};
+		cudaMemcpyToSymbol(g_amd_timing, z, sizeof(z));
+	}
+	return 0;
+}
+#endif
 
 cudaError_t init_bc7amd_tables() {
 	int dev = 0;
