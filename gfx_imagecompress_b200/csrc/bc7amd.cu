@@ -89,12 +89,27 @@ struct CubeTask {
 	uint8_t w_bits_total, w_size, w_tries, w_active;
 };
 
+// One batch (<= 32 items, one per lane) of the pruned cube walk, one lattice at a time (cube_batch)
+constexpr int kCubeBatch = 32;
+struct CubeBatch {
+	uint64_t tab[kCubeBatch][12];        // this lattice's ramp tables per item: [channel * 4 + endpoint combination]
+	uint64_t mask[kCubeBatch];           // this lattice's surviving corners per item
+	unsigned long long best[kCubeBatch]; // running best per item: key << 32 | lattice << 6 | corner
+	uint16_t unit_base[kCubeBatch + 1];
+	uint8_t task_of[kCubeBatch];
+};
+
 struct WarpScratch {
 	float in[64];
 	BlockInput B;
-	real serr[64][3];
-	uint64_t qidx[64][3]; // quantiser indices of every (partition, subset) of the running mode
-	real perr[64];
+	union {
+		struct { // quantise phase -> ranking -> task set-up
+			real serr[64][3];
+			uint64_t qidx[64][3]; // quantiser indices of every (partition, subset) of the running mode
+			real perr[64];
+		};
+		CubeBatch cb; // cube phase (the quantiser results are dead by then)
+	};
 	int top[8];
 	ShakeOut so[kMaxTasks];
 	union {
@@ -121,7 +136,7 @@ struct AmdParams {
 	int first;             // first launch of the sequence: nothing to compare with
 	int zsplit_single, zsplit_dual; // experiment knobs: 0 = auto / built-in choice
 	int split_n;                    // cube items of subsets with >= split_n texels are shared by two lanes (0 = never)
-	int prune;                      // 1: per-lane exact branch-and-bound in the cube walk (measured slower than the exhaustive walk)
+	int prune;                      // cube walk: 0 exhaustive, 1 per-lane branch-and-bound, 2 two-phase branch-and-bound (cube_batch)
 };
 
 __device__ __forceinline__ uint64_t pack_idx(const int *idx, int n) {
@@ -164,8 +179,141 @@ __device__ __noinline__ void cube_begin_pass(const Tables &T, CubeTask &t, uint6
 	t.pass_idx = 0;
 }
 
+__device__ __forceinline__ int item_owner(const WarpScratch &ws, int ntasks, int it) {
+	int ti = 0;
+	for (int r = 0; r < ntasks; r++) {
+		const int cand = ws.order[r];
+		const int base = ws.task[cand].item_base;
+		if (it >= base && it < base + ws.task[cand].item_count) ti = cand;
+	}
+	return ti;
+}
+
+// ---- exact branch-and-bound of the cube walk, organised for SIMT ------------------------------------------------
+// (bound and proof: cube_search_pruned_u8 in bc7amd_int.cuh.)  A batch is <= 32 items, one per lane.  Per lattice:
+//   A  every lane: the ramp tables of its item (to shared memory), the twelve per-channel bounds, the exact error of
+//      the corner with the smallest bound, and the mask of corners whose bound does not exceed the item's best so far
+//      (over the lattices already finished: later lattices are pruned almost completely);
+//   B  the surviving corners of ALL items form one list that is cut into 32 equal runs -- every lane evaluates the
+//      same number of corners whatever its own item pruned; results meet in a 64-bit atomicMin per item.
+// Only corners that can neither win nor tie are skipped, so the keys are those of the exhaustive walk.
+template <int CLOG>
+__device__ __forceinline__ void cube_batch_t(WarpScratch &ws, int ntasks, int b0, int b1, unsigned lane) {
+	constexpr int C = 1 << CLOG;
+	CubeBatch &cb = ws.cb;
+	const int it = b0 + (int) lane;
+	const bool have = it < b1;
+	int qp = 0, ti = 0, nl = 0, use_par = 0, bcc = 0;
+	int fl[2][3][2];
+	int bits[3] = {0, 0, 0};
+	if (have) {
+		ti = item_owner(ws, ntasks, it);
+		const CubeTask &t = ws.task[ti];
+		qp = it - t.item_base;
+		int q, p;
+		qp_decode(qp, t.Mi, C - 1, q, p);
+		cb.task_of[lane] = (uint8_t) ti;
+		ClusterAcc<CLOG> cs;
+		cluster_acc<CLOG>(t.d, t.n, t.cur, q, p, cs);
+		real epa[2][4];
+		fit_endpoints_acc<CLOG>(cs, 3, epa);
+		bits[0] = bits[1] = bits[2] = t.bits;
+		use_par = (t.type == BCC || t.type == SAME_PAR) ? 1 : 0;
+		bcc = (t.type == BCC) ? 1 : 0;
+		cube_floors(epa, bits, use_par, fl);
+		nl = (use_par + 1) * (bcc + 1);
+	}
+	const int nl_max = __reduce_max_sync(FULL, nl);
+	uint32_t best_key = 0xffffffffu, best_code = 0xffffffffu;
+	uint32_t win_pal[C];
+#pragma unroll
+	for (int c = 0; c < C; c++) win_pal[c] = 0;
+#pragma unroll 1
+	for (int l = 0; l < nl_max; l++) {
+		// ---- phase A
+		uint64_t mask = 0;
+		if (have && l < nl) {
+			const CubeTask &t = ws.task[ti];
+			const int odd = l / (bcc + 1), flip = l - odd * (bcc + 1);
+			uint32_t lb[12], ep_unused[3];
+			cube_lattice_setup<CLOG>(t.d, t.n, bits, fl, use_par, odd, flip, cb.tab[lane], lb, ep_unused);
+			const int sc = cube_seed_corner(lb);
+			if (cube_corner_bound(lb, sc) <= (best_key >> 8)) {
+				const uint32_t before = best_key;
+				cube_corner_u8<CLOG>(t.d, t.n, reinterpret_cast<const uint64_t(*)[4]>(cb.tab[lane]), sc & 3, (sc >> 2) & 3, sc >> 4, l, best_key, win_pal);
+				if (best_key != before) best_code = (uint32_t) ((l << 6) | sc);
+			}
+			mask = cube_survivors(lb, best_key >> 8) & ~(1ull << sc);
+		}
+		cb.mask[lane] = mask;
+		cb.best[lane] = ((unsigned long long) best_key << 32) | best_code;
+		const int mine = __popcll(mask);
+		int incl = mine;
+		for (int dlt = 1; dlt < 32; dlt <<= 1) {
+			const int v = __shfl_up_sync(FULL, incl, dlt);
+			if ((int) lane >= dlt) incl += v;
+		}
+		const int units = __shfl_sync(FULL, incl, 31);
+		cb.unit_base[lane] = (uint16_t) (incl - mine);
+		if (lane == 31) cb.unit_base[kCubeBatch] = (uint16_t) units;
+		__syncwarp();
+		// ---- phase B
+		const int chunk = (units + 31) >> 5;
+		const int u0 = (int) lane * chunk, u1 = min(units, u0 + chunk);
+		if (u0 < u1) {
+			int lo = 0, hi = kCubeBatch;
+			while (hi - lo > 1) {
+				const int mid = (lo + hi) >> 1;
+				if ((int) cb.unit_base[mid] <= u0) lo = mid;
+				else hi = mid;
+			}
+			int item = lo;
+			uint64_t rem = cb.mask[item];
+			for (int k = u0 - (int) cb.unit_base[item]; k > 0; k--) rem &= rem - 1;
+			for (int u = u0; u < u1; u++) {
+				while (rem == 0) {
+					item++;
+					rem = cb.mask[item];
+				}
+				const int corner = __ffsll((long long) rem) - 1;
+				rem &= rem - 1;
+				const CubeTask &t = ws.task[cb.task_of[item]];
+				uint32_t key = 0xffffffffu, pal_unused[C];
+				cube_corner_u8<CLOG>(t.d, t.n, reinterpret_cast<const uint64_t(*)[4]>(cb.tab[item]), corner & 3, (corner >> 2) & 3, corner >> 4, l, key,
+														 pal_unused);
+				atomicMin(&cb.best[item], ((unsigned long long) key << 32) | (unsigned long long) ((l << 6) | corner));
+			}
+		}
+		__syncwarp();
+		// ---- a corner of this lattice won: keep its palette (the tables are overwritten by the next lattice)
+		if (have) {
+			const unsigned long long v = cb.best[lane];
+			const uint32_t code = (uint32_t) v;
+			if ((uint32_t) (v >> 32) != best_key || code != best_code) {
+				best_key = (uint32_t) (v >> 32);
+				best_code = code;
+				const int corner = (int) (code & 63u);
+				const uint64_t t0 = cb.tab[lane][corner & 3], t1 = cb.tab[lane][4 + ((corner >> 2) & 3)], t2 = cb.tab[lane][8 + (corner >> 4)];
+#pragma unroll
+				for (int c = 0; c < C; c++) win_pal[c] = byte_of(t0, c) | (byte_of(t1, c) << 8) | (byte_of(t2, c) << 16);
+			}
+		}
+		__syncwarp();
+	}
+	if (have) {
+		const CubeTask &t = ws.task[ti];
+		ws.item_key[it - b0] = ((uint64_t) (best_key >> 8) << 16) | ((uint64_t) qp << 8) | (uint64_t) (best_key & 255u);
+		ws.item_idx[it - b0] = palette_indices_u8<CLOG>(t.d, t.n, win_pal);
+	}
+	__syncwarp();
+}
+__device__ __noinline__ void cube_batch(WarpScratch &ws, int ntasks, int clog, int b0, int b1, unsigned lane) {
+	if (clog == 2) cube_batch_t<2>(ws, ntasks, b0, b1, lane);
+	else cube_batch_t<3>(ws, ntasks, b0, b1, lane);
+}
+
 // ep_shaker_d for all tasks of the warp (u8 path). On return task[i].err_o / best_idx hold its result.
-__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit_in, unsigned lane, bool prune, int split_n) {
+__device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int ntasks, int zsplit_in, unsigned lane, int prune, int split_n) {
 	int zsplit = zsplit_in > 0 ? zsplit_in : 1;
 	if ((int) lane < ntasks) {
 		CubeTask &t = ws.task[lane];
@@ -195,6 +343,7 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 		// an item of a big subset is shared by two ADJACENT lanes, each summing half of the texels: the tasks are laid out
 		// by descending size, so the split ones come first and every pair starts on an even item (batches and rounds
 		// are even too)
+		if (prune == 2) { zsplit = 1; split = 1; } // corners, not z-slices or texel halves, are the grain of the pruned walk
 		count *= zsplit * split;
 		int rank = 0;
 		for (int o = 0; o < ntasks; o++) {
@@ -221,9 +370,11 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 		AMD_COUNT(6, total);
 		AMD_COUNT(7, (total + 31) / 32);
 		AMD_COUNT(10, 1);
-		for (int b0 = 0; b0 < total; b0 += kItemBatch) {
-			const int b1 = min(total, b0 + kItemBatch);
-			for (int it = b0 + (int) lane; it < b1; it += 32) {
+		const int batch = prune == 2 ? kCubeBatch : kItemBatch;
+		for (int b0 = 0; b0 < total; b0 += batch) {
+			const int b1 = min(total, b0 + batch);
+			if (prune == 2) cube_batch(ws, ntasks, ws.task[0].clog, b0, b1, lane);
+			else for (int it = b0 + (int) lane; it < b1; it += 32) {
 				int ti = 0;
 				for (int r = 0; r < ntasks; r++) {
 					const int cand = ws.order[r];
@@ -242,8 +393,8 @@ __device__ __noinline__ void cube_phase(const Tables &T, WarpScratch &ws, int nt
 				uint32_t key;
 				uint64_t idx;
 				const unsigned pm = split_n > 0 ? __activemask() : 0u;
-				if (t.clog == 2) cube_item_u8<2>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx, prune, half, pm);
-				else cube_item_u8<3>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx, prune, half, pm);
+				if (t.clog == 2) cube_item_u8<2>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx, prune == 1, half, pm);
+				else cube_item_u8<3>(t.d, t.n, t.cur, q, p, bits, t.type, zp * zn, zp * zn + zn, key, idx, prune == 1, half, pm);
 				ws.item_key[it - b0] = ((uint64_t) (key >> 8) << 16) | ((uint64_t) qp << 8) | (uint64_t) (key & 255u);
 				ws.item_idx[it - b0] = idx;
 			}
@@ -306,15 +457,6 @@ __device__ __forceinline__ int layout_items(WarpScratch &ws, int ntasks, int cou
 	}
 	__syncwarp();
 	return total;
-}
-__device__ __forceinline__ int item_owner(const WarpScratch &ws, int ntasks, int it) {
-	int ti = 0;
-	for (int r = 0; r < ntasks; r++) {
-		const int cand = ws.order[r];
-		const int base = ws.task[cand].item_base;
-		if (it >= base && it < base + ws.task[cand].item_count) ti = cand;
-	}
-	return ti;
 }
 
 // Start a round of ep_shaker_2_d for one task (:785-827): collapse, single-index case.
@@ -563,7 +705,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 				// shake_subset (:709-805): ep_shaker_d, ep_shaker_2_d on the quantiser's indices, and where the former
 				// won, ep_shaker_2_d again on its indices
 				AMD_T(1);
-				if (cube_u8) cube_phase(T, ws, ntasks, p.zsplit_single ? p.zsplit_single : (subsets == 3 ? 1 : 0), lane, p.prune != 0, p.split_n); // 3 subsets: small n, the per-item endpoint fit outweighs fuller rounds (measured)
+				if (cube_u8) cube_phase(T, ws, ntasks, p.zsplit_single ? p.zsplit_single : (subsets == 3 ? 1 : 0), lane, p.prune, p.split_n); // 3 subsets: small n, the per-item endpoint fit outweighs fuller rounds (measured)
 				AMD_T(2);
 				window_phase(T, ws, ntasks, lane);
 				AMD_T(3);
@@ -680,7 +822,7 @@ __global__ void __launch_bounds__(kWarps * 32, MINB) bc7amd_kernel(const AmdPara
 			}
 			__syncwarp();
 			if (U8) {
-				cube_phase(T, ws, ntasks, p.zsplit_dual ? p.zsplit_dual : (ntasks <= 8 ? 4 : 2), lane, p.prune != 0, 0);
+				cube_phase(T, ws, ntasks, p.zsplit_dual ? p.zsplit_dual : (ntasks <= 8 ? 4 : 2), lane, p.prune == 1 ? 1 : 0, 0);
 				if ((int) lane < ntasks) {
 					CubeTask &t = ws.task[lane];
 					t.w_index = t.best_idx;
@@ -866,8 +1008,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 									img.format == B200IC_FMT_RGB8_SRGB || img.format == B200IC_FMT_RGBA8 || img.format == B200IC_FMT_RGBA8_SRGB ||
 									img.format == B200IC_FMT_BLOCKS_RGBA8;
 	static const int variant = getenv("B200IC_AMD_VARIANT") ? atoi(getenv("B200IC_AMD_VARIANT")) : 3;
-	static const int fused = getenv("B200IC_AMD_FUSED") ? atoi(getenv("B200IC_AMD_FUSED")) : 0;
-	static const int serial_mask = getenv("B200IC_AMD_SERIAL") ? (int) strtol(getenv("B200IC_AMD_SERIAL"), nullptr, 0) : 0x70;
+	const int fused = getenv("B200IC_AMD_FUSED") ? atoi(getenv("B200IC_AMD_FUSED")) : 0;
+	const int serial_mask = getenv("B200IC_AMD_SERIAL") ? (int) strtol(getenv("B200IC_AMD_SERIAL"), nullptr, 0) : 0x70;
 	// One launch per mode, in the reference's visiting order {6,4,3,1,2,0,7,5} (src/amd_bc7_body.cpp:1400), the running
 	// best block and its error carried in dst / best_err: every SM then runs ONE mode's code at a time.  The fused
 	// all-modes launch is 13 % (opaque) to 26 % (translucent) slower than the sum of its single-mode launches

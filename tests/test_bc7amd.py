@@ -111,3 +111,21 @@ def test_config3_sampled_rows(engine, ref):
         want = ref.encode(BC7, px, synth.FMT_RGBA8, rows=(r, r + 1))
         rows = np.ascontiguousarray(px[4 * r:4 * r + 4])
         _check(f"block-row {r}", got[r * bx:(r + 1) * bx], want, rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("knob", ["B200IC_AMD_PRUNE=1", "B200IC_AMD_PRUNE=2", "B200IC_AMD_SPLITN=6", "B200IC_AMD_ZS=2", "B200IC_AMD_SERIAL=0"])
+def test_search_variants_are_exact(engine, knob):
+    """The scheduling variants of the shake phases (branch-and-bound cube walks, texel-half / z-slice splits of the work
+    items, warp-per-block instead of thread-per-block for modes 4-6) only reorder or skip provably losing work: the
+    blocks must be the same bytes."""
+    import os
+    px = synth.rgba8_gradnoise(128, 64, 3, "lefthalf")
+    base = engine.encode_host(engine.BC7_AMD, px, synth.FMT_RGBA8)
+    k, v = knob.split("=")
+    os.environ[k] = v
+    try:
+        got = engine.encode_host(engine.BC7_AMD, px, synth.FMT_RGBA8)
+    finally:
+        del os.environ[k]
+    assert np.array_equal(got, base)
