@@ -671,13 +671,15 @@ A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int
 					const int e1 = expand_bits(mb, p1);
 #pragma unroll 1
 					for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
-						uint64_t rv[W];
-						ramp_bytes<CLOG>(e1, expand_bits(mb, p2), rv);
-						// sum_m (rv[cidx[m]] - d[m])^2 == sum d^2 + sum_c rv_c * (cnt_c * rv_c - 2 * S1_c)
+						// ramp entry c = (2 D e1 + D + 2 c (e2 - e1)) / (2 D) (ramp_bytes), used straight from the quotient;
+						// sum_m (r[cidx[m]] - d[m])^2 == sum d^2 + sum_c r_c * (cnt_c * r_c - 2 * S1_c)
+						int num = 2 * Mi_ * e1 + Mi_;
+						const int dnum = 2 * (expand_bits(mb, p2) - e1);
 						int t = sqj;
 #pragma unroll
 						for (int c = 0; c < C; c++) {
-							const int r = (int) byte_of(rv[c >> 3], c & 7);
+							const int r = (int) ((uint32_t) num / (uint32_t) (2 * Mi_));
+							num += dnum;
 							t += r * (cnt[c] * r - sum2[c]);
 						}
 						if (t < best) { best = t; b1 = p1; b2 = p2; }
