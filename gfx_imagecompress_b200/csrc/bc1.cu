@@ -3,7 +3,7 @@
 // Replaces the image loop of reference src/amd_bc1_compressor.cpp:44-71 (gather via block_utils.cpp:7-41) and
 // Image_CompressAMDBC1Block (src/amd_bcx_helpers.cpp:51-105); the search is bc1_core.cuh.
 //
-// Mapping: one 4x4 block per thread. The search is a data-dependent fixed-point iteration (axis refit until the error
+// Mapping: one 4x4 block per PAIR of adjacent threads (the 3-point fit on one, the 4-point fit on the other). The search is a data-dependent fixed-point iteration (axis refit until the error
 // stops improving by 0.001) over FP32 sums whose order is part of the result, so the block axis is the parallel
 // axis: consecutive threads take consecutive blocks of a block-row, texel rows of a warp are contiguous 512-byte
 // runs (128-bit load per thread for RGBA8), each thread stores its 8-byte block as one 64-bit vector.
@@ -27,8 +27,11 @@ struct Bc1Params {
 };
 
 __global__ void __launch_bounds__(kThreads) bc1_kernel(const Bc1Params p) {
-	const uint64_t block = (uint64_t) blockIdx.x * kThreads + threadIdx.x;
-	if (block >= p.n_blocks) return;
+	// two adjacent lanes per block: the 3-point and the 4-point fit are independent until the final comparison
+	const uint64_t tid = (uint64_t) blockIdx.x * kThreads + threadIdx.x;
+	const uint64_t block = tid >> 1;
+	const int which = (int) (tid & 1u);
+	if (block >= p.n_blocks) return; // (pairs never straddle: kThreads is even)
 	const uint64_t per_slice = (uint64_t) p.img.blocks_x * p.img.blocks_y;
 	const uint32_t slice = (uint32_t) (block / per_slice);
 	const uint32_t rem = (uint32_t) (block - (uint64_t) slice * per_slice);
@@ -58,9 +61,17 @@ __global__ void __launch_bounds__(kThreads) bc1_kernel(const Bc1Params p) {
 			in[i * 4 + 0] = f.x; in[i * 4 + 1] = f.y; in[i * 4 + 2] = f.z; in[i * 4 + 3] = f.w;
 		}
 	}
-	uint32_t out[2];
-	bc1::encode_block(in, p.alpha_threshold, p.steps, out);
-	p.dst[block] = make_uint2(out[0], out[1]);
+	uint8_t ep[3][2], idx[16];
+	const double e = bc1::fit_half(in, which, p.alpha_threshold, p.steps, ep, idx);
+	const unsigned pm = __activemask();
+	const double other = __shfl_xor_sync(pm, e, 1);
+	const double e3 = which ? other : e, e4 = which ? e : other;
+	const int m = (e3 <= e4) ? 0 : 1; // (:89) -- an exact 3-point fit (e3 == 0) wins whatever the 4-point error is
+	if (m == which) {
+		uint32_t out[2];
+		bc1::pack_fit(m, ep, idx, out);
+		p.dst[block] = make_uint2(out[0], out[1]);
+	}
 }
 
 } // namespace
@@ -73,7 +84,7 @@ cudaError_t launch_bc1(const SrcImage &img, const b200ic_opts &opts, void *dst, 
 	p.alpha_threshold = opts.bc1_alpha_threshold;
 	p.steps = opts.amd_refinement_steps;
 	if (p.n_blocks == 0) return cudaSuccess;
-	const uint64_t grid = (p.n_blocks + kThreads - 1) / kThreads;
+	const uint64_t grid = (2 * p.n_blocks + kThreads - 1) / kThreads;
 	bc1_kernel<<<(unsigned) grid, kThreads, 0, stream>>>(p);
 	return cudaGetLastError();
 }

@@ -416,6 +416,22 @@ B1_HDN float compress(const float in[64], int np, bool use_alpha, float thr, int
 	return err;
 }
 
+// The two halves of Image_CompressAMDBC1Block for a lane pair: `which` 0 = the 3-point fit, 1 = the 4-point fit (the
+// reference skips the latter when the former is exact; its result cannot win then, e3 = 0 <= e4, so running it anyway
+// changes nothing).  pack_fit() is the selection and packing (:89-104) from the two errors.
+B1_HD double fit_half(const float in[64], int which, float alpha_threshold, int steps, uint8_t ep[3][2], uint8_t idx[16]) {
+	return (double) compress(in, which ? 4 : 3, alpha_threshold > 0.0f, alpha_threshold, steps, ep, idx);
+}
+B1_HD void pack_fit(int m, const uint8_t ep[3][2], const uint8_t idx[16], uint32_t out[2]) {
+	const uint32_t c0 = ((uint32_t) (ep[2][0] >> 3) << 11) | ((uint32_t) (ep[1][0] >> 2) << 5) | (uint32_t) (ep[0][0] >> 3);
+	const uint32_t c1 = ((uint32_t) (ep[2][1] >> 3) << 11) | ((uint32_t) (ep[1][1] >> 2) << 5) | (uint32_t) (ep[0][1] >> 3);
+	if ((m == 1 && c0 <= c1) || (m == 0 && c0 > c1)) out[0] = c1 | (c0 << 16);
+	else out[0] = c0 | (c1 << 16);
+	uint32_t bits = 0;
+	for (int i = 0; i < 16; i++) bits |= (uint32_t) idx[i] << (2 * i);
+	out[1] = bits;
+}
+
 // Image_CompressAMDBC1Block (:51-105) with adaptiveColourWeights = threeDRefinement = false
 B1_HD void encode_block(const float in[64], float alpha_threshold, int steps, uint32_t out[2]) {
 	uint8_t ep[2][3][2], idx[2][16];
