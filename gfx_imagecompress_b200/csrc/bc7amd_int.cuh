@@ -32,6 +32,16 @@ A7_HD uint32_t sq_dist4(uint32_t a, uint32_t b) { // sum over the 4 bytes of (a_
 #endif
 }
 A7_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// byte `pos` (0..3) of `into` replaced by byte c (0..7) of the ramp-table word `tab`: one PRMT on the GPU
+template <int POS> A7_HD uint32_t put_ramp_byte(uint32_t into, uint64_t tab, int c) {
+#if defined(__CUDA_ARCH__)
+	const uint32_t w = c < 4 ? (uint32_t) tab : (uint32_t) (tab >> 32);
+	const uint32_t keep = 0x3210u & ~(0xfu << (4 * POS));
+	return __byte_perm(into, w, keep | ((4u + (uint32_t) (c & 3)) << (4 * POS)));
+#else
+	return (into & ~(0xffu << (8 * POS))) | ((uint32_t) ((tab >> (8 * c)) & 255u) << (8 * POS));
+#endif
+}
 A7_HD uint32_t byte_of(uint64_t v, int i) { return (uint32_t) (v >> (8 * i)) & 255u; }
 
 // ramp values of all C entries between two EXPANDED endpoints, one byte each (C <= 8 fits a u64; C = 16 uses two)
@@ -226,13 +236,15 @@ A7_HD void cube_search_u8(const uint32_t *d, int n, const int *bits, const real 
 #pragma unroll 1
 				for (int y = 0; y < 4; y++) {
 					uint32_t pzy[C];
+					const uint64_t tz = tab[2][z], ty = tab[1][y];
 #pragma unroll
-					for (int c = 0; c < C; c++) pzy[c] = (byte_of(tab[2][z], c) << 16) | (byte_of(tab[1][y], c) << 8);
+					for (int c = 0; c < C; c++) pzy[c] = put_ramp_byte<2>(put_ramp_byte<1>(0u, ty, c), tz, c);
 #pragma unroll
 					for (int x = 0; x < 4; x++) {
 						uint32_t pal[C];
+						const uint64_t tx = tab[0][x];
 #pragma unroll
-						for (int c = 0; c < C; c++) pal[c] = pzy[c] | byte_of(tab[0][x], c);
+						for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<0>(pzy[c], tx, c);
 						uint32_t err = 0;
 #pragma unroll 1
 						for (int i = i0; i < i1; i++) {
