@@ -556,6 +556,115 @@ A7_HDN void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, in
 #endif
 }
 
+// ---- lane = corner form of the cube walk (the CUDA cube kernel of bc7amd.cu) ----------------------------------------
+// One work item = one (q, p) re-indexing of one task.  Its set-up runs on one lane per item (32 items at a time); the
+// ramp tables of all its lattices are then built by the 32 lanes together, and the (lattices x 64) corners are dealt
+// one per lane, so that every lane of the warp shares the texels, the trip count n and the tables.
+//   cube_item_setup_u8 : cluster statistics, least-squares endpoints, floors on both parity lattices; result = the
+//                        EXPANDED endpoint candidates of every (endpoint e, channel k), ep[e * 3 + k] =
+//                        bytes { parity 0: floor, neighbour ; parity 1: floor, neighbour }
+//   cube_tab_word      : 4 consecutive entries of one ramp of one lattice (table slot [lattice][k * 4 + x], x = ei0 + 2 ei1)
+//   cube_lane_corners  : the corners of lane `lane` (2 .. 8 of them), min key and its (x, y)
+//   cube_lane_palette  : palette of the lane's corner (x, y)
+template <int CLOG> A7_HD void cube_item_setup_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, int bits, int use_par, uint32_t ep_out[6]) {
+	ClusterAcc<CLOG> cs;
+	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
+	real epa[2][4];
+	fit_endpoints_acc<CLOG>(cs, 3, epa);
+	const int top = (1 << bits) - 1, reach = 1 << use_par;
+#pragma unroll 1
+	for (int e = 0; e < 2; e++)
+#pragma unroll 1
+		for (int k = 0; k < 3; k++) {
+			uint32_t w = 0;
+#pragma unroll 1
+			for (int par = 0; par <= use_par; par++) {
+				const int f = endpoint_floor(epa[e][k], bits, use_par, par);
+				const int up = f + ((top - f < reach ? top - f : reach) & ~use_par);
+				w |= ((uint32_t) expand_bits(bits, f) | ((uint32_t) expand_bits(bits, up) << 8)) << (16 * par);
+			}
+			ep_out[e * 3 + k] = w;
+		}
+}
+template <int CLOG> A7_HD uint32_t ramp_word(int e1, int e2, int c0) { // entries c0 .. c0 + 3 of ramp_bytes
+	constexpr int D = (1 << CLOG) - 1;
+	const int step = 2 * (e2 - e1);
+	int num = 2 * D * e1 + D + c0 * step; // = 2 (D - c) e1 + 2 c e2 + D >= 0
+	uint32_t w = 0;
+#pragma unroll
+	for (int c = 0; c < 4; c++) {
+		w |= ((uint32_t) num / (uint32_t) (2 * D)) << (8 * c);
+		num += step;
+	}
+	return w;
+}
+// word `id` of the item's tables: id = (lattice * 12 + k * 4 + x) * H + half, H = C / 4 words per ramp
+template <int CLOG> A7_HD uint32_t cube_tab_word(const uint32_t ep[6], int bcc, int id) {
+	constexpr int H = (1 << CLOG) / 4;
+	const int hf = id % H, rid = id / H;
+	const int x = rid & 3, lk = rid >> 2, l = lk / 3, k = lk - 3 * l;
+	const int odd = bcc ? (l >> 1) : l, flip = bcc ? (l & 1) : 0;
+	const int e1 = (int) ((ep[k] >> (16 * odd + 8 * (x & 1))) & 255u), e2 = (int) ((ep[3 + k] >> (16 * (odd ^ flip) + 8 * (x >> 1))) & 255u);
+	return ramp_word<CLOG>(e1, e2, 4 * hf);
+}
+// Corner -> lane map, nlb = log2(lattices): lane bits (LSB first) = lattice (nlb bits), z (2), then
+//   nlb 2: y bit 0          ; the lane walks y bit 1 (outer) and x (inner) : 8 corners
+//   nlb 1: y                ; the lane walks x                             : 4 corners
+//   nlb 0: y, x bit 0       ; the lane walks x bit 1                       : 2 corners
+// key = err << 8 | lattice << 6 | gray position (gray_position is linear over GF(2): one XOR per corner)
+template <int CLOG>
+A7_HD void cube_lane_corners(const uint64_t *tab, const uint32_t (&d)[16], int n, int nlb, unsigned lane, uint32_t &best_key, uint32_t &best_xy) {
+	constexpr int C = 1 << CLOG;
+	const int l = (int) lane & ((1 << nlb) - 1), rest = (int) lane >> nlb;
+	const int z = rest & 3;
+	const int yb = nlb == 2 ? ((rest >> 2) & 1) : ((rest >> 2) & 3), xb = nlb == 0 ? ((rest >> 4) & 1) : 0;
+	const int outer = nlb == 2 ? 2 : 1, inner = nlb == 0 ? 2 : 4, xstep = nlb == 0 ? 2 : 1;
+	const uint64_t *tl = tab + l * 12;
+	const uint64_t tz = tl[8 + z];
+	const uint32_t gz = (uint32_t) gray_position(z << 4) | ((uint32_t) l << 6);
+	best_key = 0xffffffffu;
+	best_xy = 0;
+#pragma unroll 1
+	for (int o = 0; o < outer; o++) {
+		const int y = yb | (o << 1);
+		const uint64_t ty = tl[4 + y];
+		uint32_t pzy[C];
+#pragma unroll
+		for (int c = 0; c < C; c++) pzy[c] = put_ramp_byte<2>(put_ramp_byte<1>(0u, ty, c), tz, c);
+		const uint32_t gzy = gz ^ (uint32_t) gray_position(y << 2);
+#pragma unroll 1
+		for (int i = 0; i < inner; i++) {
+			const int x = xb + i * xstep;
+			const uint64_t tx = tl[x];
+			uint32_t pal[C];
+#pragma unroll
+			for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<0>(pzy[c], tx, c);
+			uint32_t err = 0;
+#pragma unroll
+			for (int t = 0; t < 16; t++)
+				if (t < n) {
+					uint32_t m = sq_dist4(pal[0], d[t]);
+#pragma unroll
+					for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], d[t]));
+					err += m;
+				}
+			const uint32_t key = (err << 8) | (gzy ^ (uint32_t) gray_position(x));
+			if (key < best_key) {
+				best_key = key;
+				best_xy = (uint32_t) (x | (y << 2));
+			}
+		}
+	}
+}
+template <int CLOG> A7_HD void cube_lane_palette(const uint64_t *tab, int nlb, unsigned lane, uint32_t xy, uint32_t *pal) {
+	constexpr int C = 1 << CLOG;
+	const int l = (int) lane & ((1 << nlb) - 1), z = ((int) lane >> nlb) & 3;
+	const uint64_t *tl = tab + l * 12;
+	const uint64_t tx = tl[xy & 3u], ty = tl[4 + ((xy >> 2) & 3u)], tz = tl[8 + z];
+#pragma unroll
+	for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<2>(put_ramp_byte<1>(put_ramp_byte<0>(0u, tx, c), ty, c), tz, c);
+}
+
 // ep_shaker_d on packed 8-bit data (dimension 3). index_io in/out; returns the SSE (exact integer as real).
 template <int CLOG>
 A7_HDN real shake_cube_u8(const Tables &T, const U8Subset &S, int *index_io, const int *bits, int type) {

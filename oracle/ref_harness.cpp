@@ -2,10 +2,11 @@
 // sources, which oracle/Makefile compiles from /root/reference/src where they lie into
 // oracle/_ref/libref_oracle.so. Nothing here is on the product path.
 //
-// The reference is single-threaded; this harness splits an image into horizontal strips of whole
-// block-rows and calls the reference's own image-level API (Image_CompressAMDBC1 ... ,
-// include/gfx_imagecompress/imagecompress.h:69-100) on each strip from its own std::thread after one
-// Image_CompressInit(). Blocks are independent, so the strip output is byte-identical
+// The reference is single-threaded; this harness splits an image into tiles of whole 4x4 blocks (block-row chunks,
+// cut into block-column segments when block-rows alone would leave threads idle) and calls the reference's own
+// image-level API (Image_CompressAMDBC1 ... ,
+// include/gfx_imagecompress/imagecompress.h:69-100) on each tile from a pool of std::threads after one
+// Image_CompressInit(). Blocks are independent, so the tiled output is byte-identical
 // to a serial call.
 #include "al2o3_platform/platform.h"
 #include "gfx_image/image.h"
@@ -60,9 +61,16 @@ static Image_ImageHeader const *encode_one(int codec, Image_ImageHeader const *s
 	}
 }
 
+// Threads that encoded at least one work unit in the last ref_encode_rows call (bench.py reports it beside `cores`).
+static std::atomic<int> g_threads_used{0};
+int ref_last_threads_used() { return g_threads_used.load(); }
+
 // Encode block-rows [by0, by1) of a tightly packed w x h image (one slice) in format `fmt`
 // (a TinyImageFormat value of the compat shim). `dst` receives (by1-by0)*blocksX blocks.
-// Returns 0 on success.
+// Work units are tiles of whole 4x4 blocks: chunks of block-rows, cut further into block-column segments when there
+// are fewer block-rows than 8 x nthreads, so that EVERY thread has work even for a sample of a few block-rows (only the
+// last segment of a row can end off a multiple of 4 -- at the true image edge -- so the replicate-edge gather of
+// src/block_utils.cpp:19,22 sees the same texels as in a whole-image call). Returns 0 on success.
 int ref_encode_rows(int codec, void const *pixels, uint32_t w, uint32_t h, int fmt, uint32_t by0, uint32_t by1,
 										void *dst, int nthreads, ref_opts const *opts) {
 	TinyImageFormat const tf = (TinyImageFormat) fmt;
@@ -73,30 +81,46 @@ int ref_encode_rows(int codec, void const *pixels, uint32_t w, uint32_t h, int f
 	if (by0 >= by1) return 0;
 	uint32_t const nrows = by1 - by0;
 	if (nthreads < 1) nthreads = 1;
-	nthreads = (int) std::min<uint32_t>((uint32_t) nthreads, nrows);
 	uint32_t const blockBytes = (codec == REF_BC1 || codec == REF_BC4) ? 8 : 16;
+	uint32_t const want_units = (uint32_t) nthreads * 8;
+	uint32_t const row_chunk = std::max<uint32_t>(1, nrows / want_units);
+	uint32_t const row_units = (nrows + row_chunk - 1) / row_chunk;
+	uint32_t segs = row_units >= want_units ? 1 : (want_units + row_units - 1) / row_units;
+	segs = std::min(segs, blocksX);
+	uint32_t const seg_blocks = (blocksX + segs - 1) / segs;
+	segs = (blocksX + seg_blocks - 1) / seg_blocks;
+	uint32_t const units = row_units * segs;
+	nthreads = (int) std::min<uint32_t>((uint32_t) nthreads, units);
 
 	Image_CompressInit();
-	std::atomic<int> failed{0};
+	std::atomic<int> failed{0}, used{0};
 	std::atomic<uint32_t> next{0};
-	// dynamic scheduling over chunks of block-rows: per-block cost is data dependent
-	uint32_t const chunk = std::max<uint32_t>(1, nrows / (uint32_t) (nthreads * 8));
 	auto worker = [&]() {
+		bool worked = false;
 		for (;;) {
-			uint32_t const c0 = next.fetch_add(chunk);
-			if (c0 >= nrows) break;
-			uint32_t const r0 = by0 + c0, r1 = std::min(by1, r0 + chunk);
+			uint32_t const u = next.fetch_add(1);
+			if (u >= units) break;
+			worked = true;
+			uint32_t const ru = u / segs, su = u - ru * segs;
+			uint32_t const c0 = ru * row_chunk;                                  // first block-row of the unit, relative to by0
+			uint32_t const r0 = by0 + c0, r1 = std::min(by1, r0 + row_chunk);
 			uint32_t const y0 = r0 * 4, y1 = std::min(h, r1 * 4);
-			Image_ImageHeader const *strip = Image_CreateNoClear(w, y1 - y0, 1, 1, tf);
-			if (!strip) { failed = 1; break; }
-			memcpy(Image_RawDataPtr(strip), (uint8_t const *) pixels + (size_t) y0 * w * bpp, (size_t) (y1 - y0) * w * bpp);
-			Image_ImageHeader const *out = encode_one(codec, strip, opts);
-			if (!out) { failed = 1; Image_Destroy(strip); break; }
-			memcpy((uint8_t *) dst + (size_t) c0 * blocksX * blockBytes, Image_RawDataPtr(out),
-						 (size_t) (r1 - r0) * blocksX * blockBytes);
+			uint32_t const bx0 = su * seg_blocks, bx1 = std::min(blocksX, bx0 + seg_blocks);
+			uint32_t const x0 = bx0 * 4, x1 = std::min(w, bx1 * 4);
+			Image_ImageHeader const *tile = Image_CreateNoClear(x1 - x0, y1 - y0, 1, 1, tf);
+			if (!tile) { failed = 1; break; }
+			for (uint32_t y = y0; y < y1; ++y)
+				memcpy((uint8_t *) Image_RawDataPtr(tile) + (size_t) (y - y0) * (x1 - x0) * bpp,
+							 (uint8_t const *) pixels + ((size_t) y * w + x0) * bpp, (size_t) (x1 - x0) * bpp);
+			Image_ImageHeader const *out = encode_one(codec, tile, opts);
+			if (!out) { failed = 1; Image_Destroy(tile); break; }
+			for (uint32_t r = r0; r < r1; ++r)
+				memcpy((uint8_t *) dst + ((size_t) (r - by0) * blocksX + bx0) * blockBytes,
+							 (uint8_t const *) Image_RawDataPtr(out) + (size_t) (r - r0) * (bx1 - bx0) * blockBytes, (size_t) (bx1 - bx0) * blockBytes);
 			Image_Destroy(out);
-			Image_Destroy(strip);
+			Image_Destroy(tile);
 		}
+		if (worked) used.fetch_add(1);
 	};
 	if (nthreads == 1) worker();
 	else {
@@ -104,6 +128,7 @@ int ref_encode_rows(int codec, void const *pixels, uint32_t w, uint32_t h, int f
 		for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker);
 		for (auto &t : pool) t.join();
 	}
+	g_threads_used = used.load();
 	return failed.load();
 }
 

@@ -40,6 +40,8 @@ def load():
         L.hb_bc1_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
     if hasattr(L, "hb_bc7amd_blocks"):
         L.hb_bc7amd_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    if hasattr(L, "hb_cube_lane_check"):
+        L.hb_cube_lane_check.argtypes = [C.c_uint64, C.c_int]
     return L
 
 

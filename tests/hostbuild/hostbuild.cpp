@@ -69,6 +69,80 @@ void hb_bc7amd_blocks(const float *in, uint64_t nblocks, uint32_t mode_mask, uin
 	for (auto &t : pool) t.join();
 }
 #endif
+#ifdef HB_BC7AMD
+// The lane = corner form of the cube walk (bc7amd_int.cuh, what the CUDA cube kernel runs) emulated lane by lane
+// against the serial cube_search_u8 on random items. Returns the number of items whose (key, indices) differ.
+}
+template <int CLOG> static int hb_cube_lane_trial(uint64_t &rng, int bits, int type) {
+	using namespace b200ic::amd7;
+	auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t) (rng >> 33); };
+	constexpr int C = 1 << CLOG;
+	const int n = 1 + (int) (next() % 16);
+	uint32_t d[16] = {};
+	const uint32_t base = next(), spread = 1u << (next() % 8);
+	for (int i = 0; i < n; i++) {
+		uint32_t v = 0;
+		for (int j = 0; j < 3; j++) v |= ((((base >> (8 * j)) & 255u) + next() % spread) & 255u) << (8 * j);
+		d[i] = v;
+	}
+	// a collapsed index vector with maximum Mi >= 1, and one of its (q, p) re-indexings
+	int idx[16], Mi = 0;
+	for (int i = 0; i < n; i++) idx[i] = (int) (next() % C);
+	idx[0] = 0;
+	if (n > 1) idx[n - 1] = 1 + (int) (next() % (C - 1));
+	else return 0;
+	Mi = collapse_indices(idx, n);
+	if (Mi == 0) return 0;
+	uint64_t cur = 0;
+	for (int i = 0; i < n; i++) cur |= (uint64_t) idx[i] << (4 * i);
+	const int count = qp_count(Mi, C - 1);
+	int q, p;
+	qp_decode((int) (next() % count), Mi, C - 1, q, p);
+	const int use_par = (type == BCC || type == SAME_PAR) ? 1 : 0, bcc = type == BCC ? 1 : 0;
+	const int b3[3] = {bits, bits, bits};
+	uint32_t want_key;
+	uint64_t want_idx;
+	cube_item_u8<CLOG>(d, n, cur, q, p, b3, type, 0, 4, want_key, want_idx);
+	// lane form
+	uint32_t ep[6];
+	cube_item_setup_u8<CLOG>(d, n, cur, q, p, bits, use_par, ep);
+	const int nl = (use_par + 1) * (bcc + 1), nlb = nl == 4 ? 2 : (nl == 2 ? 1 : 0);
+	uint64_t tab[4 * 12] = {};
+	constexpr int H = C / 4;
+	for (int id = 0; id < nl * 12 * H; id++) {
+		const uint32_t w = cube_tab_word<CLOG>(ep, bcc, id);
+		tab[id / H] |= (uint64_t) w << (32 * (id % H));
+	}
+	uint32_t best = 0xffffffffu, best_xy = 0;
+	unsigned best_lane = 0;
+	for (unsigned lane = 0; lane < 32; lane++) {
+		uint32_t k, xy;
+		cube_lane_corners<CLOG>(tab, d, n, nlb, lane, k, xy);
+		if (k < best) { best = k; best_xy = xy; best_lane = lane; }
+	}
+	uint32_t pal[C];
+	cube_lane_palette<CLOG>(tab, nlb, best_lane, best_xy, pal);
+	const uint64_t got_idx = palette_indices_u8<CLOG>(d, n, pal);
+	return (best != want_key || got_idx != want_idx) ? 1 : 0;
+}
+extern "C" {
+int hb_cube_lane_check(uint64_t seed, int trials) {
+	using namespace b200ic::amd7;
+	uint64_t rng = seed * 2 + 1;
+	int bad = 0;
+	for (int t = 0; t < trials; t++) {
+		bad += hb_cube_lane_trial<3>(rng, 5, BCC);      // mode 0
+		bad += hb_cube_lane_trial<3>(rng, 7, SAME_PAR); // mode 1
+		bad += hb_cube_lane_trial<2>(rng, 5, CART);     // mode 2
+		bad += hb_cube_lane_trial<2>(rng, 8, BCC);      // mode 3
+		bad += hb_cube_lane_trial<2>(rng, 5, CART);     // mode 4 vector
+		bad += hb_cube_lane_trial<3>(rng, 6, CART);     // mode 4 scalar (3-bit indices)
+		bad += hb_cube_lane_trial<2>(rng, 7, CART);     // mode 5 vector
+		bad += hb_cube_lane_trial<2>(rng, 8, CART);     // mode 5 scalar
+	}
+	return bad;
+}
+#endif
 #ifdef HB_BC7RG
 void hb_bc7rg_blocks(const uint32_t *px, uint64_t nblocks, int perceptual, int fast, uint8_t *out) {
 	static b200ic::rg::OptimalEndpoint table[512];
