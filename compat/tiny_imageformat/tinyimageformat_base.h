@@ -5,6 +5,10 @@
 #include <stdint.h>
 #include <stdbool.h>
 
+// the private unsigned-half tag below exists in THIS shim only; code that must also compile against upstream
+// tiny_imageformat (csrc/image_shim.cpp) tests this macro
+#define B200IC_COMPAT_HAS_R16G16B16A16_UFLOAT 1
+
 typedef enum TinyImageFormat {
 	TinyImageFormat_UNDEFINED = 0,
 	TinyImageFormat_R8_UNORM,

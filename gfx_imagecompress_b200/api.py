@@ -71,7 +71,7 @@ _lib = None
 def load_library(path: str | None = None):
     """Loads the CUDA library. Raises if it has not been built -- there is deliberately no fallback."""
     global _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("B200IC_LIB") or LIB_PATH  # B200IC_LIB: a debug build (tools/amd_phase_times.py)
     if not os.path.exists(path):
         raise B200Error(f"{path} is missing: run `python -m gfx_imagecompress_b200.build` (or __graft_entry__.build())")
     L = C.CDLL(path)
@@ -85,6 +85,10 @@ def load_library(path: str | None = None):
                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200ic_encode_host.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200ic_encode_host_sharded.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.b200ic_set_devices.argtypes = [C.c_int]
+    L.b200ic_device_count.restype = C.c_int
     L.b200ic_encode_blocks.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     L.b200ic_plan_shards.restype = C.c_uint64
     L.b200ic_plan_shards.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -107,6 +111,8 @@ def load_library(path: str | None = None):
     L.Image_CompressAMDMultiModeLDRBlock.argtypes = [C.c_void_p, C.c_uint8, C.c_bool, C.c_float, C.c_bool, C.c_bool,
                                                      C.c_float, C.c_void_p]
     L.Image_CompressRichGel999BC7enc16.argtypes = [C.c_void_p, C.c_bool, C.c_bool, C.c_void_p]
+    L.Image_CompressAMDRGBSingleModeBlock.argtypes = [C.c_void_p, C.c_bool, C.c_bool, C.c_uint8, C.c_void_p]
+    L.Image_CompressAMDExplictAlphaSingleModeBlock.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -144,9 +150,19 @@ def _geometry(pixels: np.ndarray, fmt: int):
     return s, h, w
 
 
+def device_count() -> int:
+    return int(library().b200ic_device_count())
+
+
+def set_devices(n: int) -> None:
+    """How many GPUs the Image_Compress* entry points shard a large image over (0 = all visible)."""
+    library().b200ic_set_devices(n)
+
+
 def encode_host(codec: int, pixels: np.ndarray, fmt: int, opts: Opts | None = None, out: np.ndarray | None = None,
-                progress=None) -> np.ndarray:
-    """Host-buffer encode through b200ic_encode_host (H2D + kernels + D2H inside the call).
+                progress=None, devices: int = 1) -> np.ndarray:
+    """Host-buffer encode through b200ic_encode_host (H2D + kernels + D2H inside the call); devices != 1 shards the
+    block-rows over that many GPUs of this process (b200ic_encode_host_sharded, 0 = all visible).
     pixels: ([S,] H, W, C) C-contiguous array in `fmt`. Returns uint8 (nblocks, blockBytes)."""
     L = library()
     s, h, w = _geometry(pixels, fmt)
@@ -154,8 +170,12 @@ def encode_host(codec: int, pixels: np.ndarray, fmt: int, opts: Opts | None = No
     if out is None:
         out = np.empty((nb, BLOCK_BYTES[codec]), np.uint8)
     cb = _HostProgress(progress) if progress is not None else None
-    rc = L.b200ic_encode_host(codec, pixels.ctypes.data, fmt, w, h, 0, s, C.byref(opts) if opts is not None else None,
-                              out.ctypes.data, C.cast(cb.fn, C.c_void_p) if cb else None, None)
+    if devices == 1:
+        rc = L.b200ic_encode_host(codec, pixels.ctypes.data, fmt, w, h, 0, s, C.byref(opts) if opts is not None else None,
+                                  out.ctypes.data, C.cast(cb.fn, C.c_void_p) if cb else None, None)
+    else:
+        rc = L.b200ic_encode_host_sharded(codec, pixels.ctypes.data, fmt, w, h, 0, s, C.byref(opts) if opts is not None else None,
+                                          out.ctypes.data, C.cast(cb.fn, C.c_void_p) if cb else None, None, devices)
     if rc == 1:
         return None  # cancelled
     _check(rc, "b200ic_encode_host")
@@ -294,6 +314,22 @@ def Image_CompressAMDBC1(src: Image, amdOptions=None, options=None, progress=Non
     return _wrap(library().Image_CompressAMDBC1(src.ptr, C.byref(a) if a else None, C.byref(o) if o else None, cb, None))
 
 
+def Image_CompressAMDBC2(src: Image, amdOptions=None, progress=None):
+    a = _AmdOptions(*amdOptions) if amdOptions else None
+    keep, cb = _cb(progress)
+    return _wrap(library().Image_CompressAMDBC2(src.ptr, C.byref(a) if a else None, cb, None))
+
+
+def Image_CompressAMDBC3(src: Image, amdOptions=None, progress=None):
+    a = _AmdOptions(*amdOptions) if amdOptions else None
+    keep, cb = _cb(progress)
+    return _wrap(library().Image_CompressAMDBC3(src.ptr, C.byref(a) if a else None, cb, None))
+
+
+def ImageCompress_PickCompressionType(flags: int, src: Image) -> int:
+    return int(library().ImageCompress_PickCompressionType(flags, src.ptr))
+
+
 def Image_CompressAMDBC4(src: Image, progress=None):
     keep, cb = _cb(progress)
     return _wrap(library().Image_CompressAMDBC4(src.ptr, cb, None))
@@ -356,4 +392,18 @@ def Image_CompressRichGel999BC7enc16(rgba8, fast=False, perceptual=True) -> np.n
     v = np.ascontiguousarray(rgba8, np.uint32).reshape(16)
     out = np.zeros(16, np.uint8)
     library().Image_CompressRichGel999BC7enc16(v.ctypes.data, fast, perceptual, out.ctypes.data)
+    return out
+
+
+def Image_CompressAMDRGBSingleModeBlock(rgb, adaptive=False, refine3d=False, steps=1) -> np.ndarray:
+    v = np.ascontiguousarray(rgb, np.float32).reshape(48)
+    out = np.zeros(8, np.uint8)
+    library().Image_CompressAMDRGBSingleModeBlock(v.ctypes.data, adaptive, refine3d, steps, out.ctypes.data)
+    return out
+
+
+def Image_CompressAMDExplictAlphaSingleModeBlock(values) -> np.ndarray:
+    v = np.ascontiguousarray(values, np.float32).reshape(16)
+    out = np.zeros(8, np.uint8)
+    library().Image_CompressAMDExplictAlphaSingleModeBlock(v.ctypes.data, out.ctypes.data)
     return out

@@ -2,7 +2,7 @@
 
 One translation unit per codec: the bit-exact codecs (BC1/BC4/BC5/bc7enc16) are compiled with --fmad=false
 so that no FP32 multiply-add is contracted (the reference's output changes under contraction),
-the AMD BC7 kernel likewise (it then reproduces the FP64 reference bit for bit); BC6H with default contraction.
+the AMD BC7 and BC6H kernels likewise (they then reproduce the FP64 / FP32 reference bit for bit).
 """
 from __future__ import annotations
 
@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "lib")
+OUT = os.environ.get("B200IC_BUILD_DIR") or os.path.join(HERE, "lib")  # (debug builds go elsewhere: B200IC_BUILD_DIR)
 LIB = os.path.join(OUT, "libgfx_imagecompress_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -25,7 +25,6 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 # (source, extra flags)
 UNITS = [
     ("api.cu", []),
-    ("stubs.cu", []),
     ("bc45.cu", ["--fmad=false"]),
     ("bc1.cu", ["--fmad=false"]),
     ("bc7rg.cu", ["--fmad=false"]),
@@ -33,9 +32,6 @@ UNITS = [
     ("bc6h.cu", ["--fmad=false"]),
     ("image_shim.cpp", []),
 ]
-HAVE = {"bc1.cu": "B200IC_HAVE_BC1", "bc7rg.cu": "B200IC_HAVE_BC7RG", "bc7amd.cu": "B200IC_HAVE_BC7AMD",
-        "bc6h.cu": "B200IC_HAVE_BC6H"}
-
 
 def nvcc() -> str:
     for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
@@ -57,8 +53,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     headers += [os.path.join(ROOT, "include", "b200ic.h"),
                 os.path.join(ROOT, "include", "gfx_imagecompress", "imagecompress.h"), os.path.abspath(__file__)]
     present = [(s, f) for s, f in UNITS if os.path.exists(os.path.join(CSRC, s))]
-    defines = ["-D" + HAVE[s] for s, _ in present if s in HAVE]
-    defines += ["-D" + d for d in os.environ.get("B200IC_EXTRA_DEFS", "").split() if d]  # e.g. B200IC_AMD_TIMING (debug builds)
+    defines = ["-D" + d for d in os.environ.get("B200IC_EXTRA_DEFS", "").split() if d]  # e.g. B200IC_AMD_TIMING (debug builds)
     cc = nvcc()
     jobs = []
     objs = []

@@ -6,8 +6,10 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace b200ic {
@@ -32,6 +34,8 @@ static int fail(const char *what, cudaError_t e = cudaSuccess) {
 static uint32_t block_bytes(int codec) {
 	switch (codec) {
 	case B200IC_BC1:
+	case B200IC_BC23_COLOUR_HALF:
+	case B200IC_BC2_ALPHA_HALF:
 	case B200IC_BC4: return 8;
 	case B200IC_BC2:
 	case B200IC_BC3:
@@ -68,25 +72,34 @@ static uint32_t blocks_format_bytes(int fmt) { // bytes per pre-gathered block
 	}
 }
 
-// ---- per-thread device context: stream ring + grow-only device scratch for the host path -------------
-struct HostCtx {
+// ---- per-device host-path context (process-wide pool): stream ring, grow-only device scratch and pinned staging ---
+// One host-path encode runs per device at a time (`mu`); the contexts outlive the calling threads, so a thread that
+// encodes and exits leaks nothing, and b200ic_shutdown() releases every device's context.
+struct DevCtx {
 	static constexpr int kStreams = 3;
+	std::mutex mu;
 	int device = -1;
 	cudaStream_t streams[kStreams] = {};
 	void *d_in[kStreams] = {};
 	void *d_out[kStreams] = {};
 	size_t in_cap[kStreams] = {};
 	size_t out_cap[kStreams] = {};
+	void *p_in[kStreams] = {};  // pinned staging for pageable caller buffers
+	void *p_out[kStreams] = {};
+	size_t pin_cap[kStreams] = {};
+	size_t pout_cap[kStreams] = {};
 	bool ready = false;
-	cudaEvent_t fork = nullptr, join[kStreams] = {};
+	cudaEvent_t fork = nullptr, join[kStreams] = {}, kdone[kStreams] = {};
 
-	int ensure(int dev) {
-		if (ready && dev == device) return 0;
-		release();
+	int ensure(int dev) { // call with `mu` held and `dev` current
+		if (ready) return 0;
 		device = dev;
-		for (int i = 0; i < kStreams; i++) B200IC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "stream create");
-		B200IC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "event create");
-		for (int i = 0; i < kStreams; i++) B200IC_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming), "event create");
+		for (int i = 0; i < kStreams; i++) {
+			if (!streams[i]) B200IC_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking), "stream create");
+			if (!join[i]) B200IC_CUDA(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming), "event create");
+			if (!kdone[i]) B200IC_CUDA(cudaEventCreateWithFlags(&kdone[i], cudaEventDisableTiming), "event create");
+		}
+		if (!fork) B200IC_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "event create");
 		ready = true;
 		return 0;
 	}
@@ -107,25 +120,50 @@ struct HostCtx {
 		}
 		return 0;
 	}
-	void release() {
-		if (!ready) return;
+	int reserve_pinned(int i, size_t in_bytes, size_t out_bytes) {
+		if (in_bytes > pin_cap[i]) {
+			if (p_in[i]) cudaFreeHost(p_in[i]);
+			p_in[i] = nullptr;
+			pin_cap[i] = 0;
+			B200IC_CUDA(cudaHostAlloc(&p_in[i], in_bytes, cudaHostAllocDefault), "cudaHostAlloc(input staging)");
+			pin_cap[i] = in_bytes;
+		}
+		if (out_bytes > pout_cap[i]) {
+			if (p_out[i]) cudaFreeHost(p_out[i]);
+			p_out[i] = nullptr;
+			pout_cap[i] = 0;
+			B200IC_CUDA(cudaHostAlloc(&p_out[i], out_bytes, cudaHostAllocDefault), "cudaHostAlloc(output staging)");
+			pout_cap[i] = out_bytes;
+		}
+		return 0;
+	}
+	void release() { // call with `mu` held
+		if (device < 0) return;
+		int prev = -1;
+		cudaGetDevice(&prev);
+		cudaSetDevice(device);
 		for (int i = 0; i < kStreams; i++) {
 			if (streams[i]) cudaStreamDestroy(streams[i]);
 			if (d_in[i]) cudaFree(d_in[i]);
 			if (d_out[i]) cudaFree(d_out[i]);
+			if (p_in[i]) cudaFreeHost(p_in[i]);
+			if (p_out[i]) cudaFreeHost(p_out[i]);
 			if (join[i]) cudaEventDestroy(join[i]);
-			join[i] = nullptr;
+			if (kdone[i]) cudaEventDestroy(kdone[i]);
+			join[i] = kdone[i] = nullptr;
 			streams[i] = nullptr;
-			d_in[i] = d_out[i] = nullptr;
-			in_cap[i] = out_cap[i] = 0;
+			d_in[i] = d_out[i] = p_in[i] = p_out[i] = nullptr;
+			in_cap[i] = out_cap[i] = pin_cap[i] = pout_cap[i] = 0;
 		}
 		if (fork) cudaEventDestroy(fork);
 		fork = nullptr;
 		ready = false;
+		device = -1;
+		if (prev >= 0) cudaSetDevice(prev);
 	}
-	~HostCtx() { /* process teardown: the driver reclaims everything */ }
 };
-static thread_local HostCtx t_ctx;
+constexpr int kMaxDevices = 16;
+static DevCtx g_ctx[kMaxDevices];
 static std::mutex g_init_mutex;
 static int g_tables_device_mask_lo = 0; // bit per device whose __constant__/global tables were uploaded
 
@@ -163,6 +201,14 @@ static int dispatch(int codec, const SrcImage &img, const b200ic_opts &o, void *
 	case B200IC_BC1:
 		if (o.amd_3d_refinement || o.amd_adaptive_weights) return fail("BC1: b3DRefinement / AdaptiveColourWeights are not supported");
 		e = launch_bc1(img, o, d_dst, stream);
+		break;
+	case B200IC_BC2:
+	case B200IC_BC3:
+	case B200IC_BC23_COLOUR_HALF:
+	case B200IC_BC2_ALPHA_HALF:
+		if (o.amd_3d_refinement || o.amd_adaptive_weights) return fail("BC2/BC3: b3DRefinement / AdaptiveColourWeights are not supported");
+		e = launch_bc23(img, o, codec == B200IC_BC3 ? kBc3Colour : (codec == B200IC_BC2 ? kBc2Both : (codec == B200IC_BC23_COLOUR_HALF ? kColourOnly : kAlphaOnly)),
+										d_dst, stream);
 		break;
 	case B200IC_BC7_RG: e = launch_bc7rg(img, o, d_dst, stream); break;
 	case B200IC_BC7_AMD: e = launch_bc7amd(img, o, d_dst, stream); break;
@@ -202,18 +248,14 @@ int b200ic_codec_available(int codec) {
 	switch (codec) {
 	case B200IC_BC4:
 	case B200IC_BC5: return 1;
-#ifdef B200IC_HAVE_BC1
-	case B200IC_BC1: return 1;
-#endif
-#ifdef B200IC_HAVE_BC7RG
+	case B200IC_BC1:
+	case B200IC_BC2:
+	case B200IC_BC3:
+	case B200IC_BC23_COLOUR_HALF:
+	case B200IC_BC2_ALPHA_HALF: return 1;
 	case B200IC_BC7_RG: return 1;
-#endif
-#ifdef B200IC_HAVE_BC7AMD
 	case B200IC_BC7_AMD: return 1;
-#endif
-#ifdef B200IC_HAVE_BC6H
 	case B200IC_BC6H: return 1;
-#endif
 	default: return 0;
 	}
 }
@@ -228,7 +270,12 @@ int b200ic_init(int device) {
 	return ensure_device();
 }
 
-void b200ic_shutdown(void) { t_ctx.release(); }
+void b200ic_shutdown(void) {
+	for (int d = 0; d < kMaxDevices; d++) {
+		std::lock_guard<std::mutex> lock(g_ctx[d].mu);
+		g_ctx[d].release();
+	}
+}
 
 const char *b200ic_last_error(void) { return t_error.c_str(); }
 
@@ -272,80 +319,228 @@ int b200ic_encode_device(int codec, const void *d_src, int format, uint32_t widt
 		img.row_pitch = row_pitch_bytes ? row_pitch_bytes : (uint64_t) width * tb;
 		img.slice_pitch = slice_pitch_bytes ? slice_pitch_bytes : img.row_pitch * height;
 		if (img.row_pitch < (uint64_t) width * tb) return fail("row pitch smaller than a row");
-		if ((tb == 4 || tb == 8 || tb == 16) && ((img.row_pitch % tb) || ((uintptr_t) d_src % tb)))
-			return fail("source rows must be aligned to the texel size");
+		// the gather uses 32- / 64- / 128-bit loads for 4- / 8- / 16-byte texels: a misaligned pointer would raise a sticky
+		// misaligned-address fault that poisons the CUDA context instead of an error return
+		if ((tb == 4 || tb == 8 || tb == 16) && ((img.row_pitch % tb) || (img.slice_pitch % tb) || ((uintptr_t) d_src % tb)))
+			return fail("source rows and slices must be aligned to the texel size");
 	}
+	if (format == B200IC_FMT_BLOCKS_RGBA8 && ((uintptr_t) d_src % 16)) return fail("RGBA8 block sources must be 16-byte aligned");
+	if (format >= 100 && format != B200IC_FMT_BLOCKS_RGBA8 && ((uintptr_t) d_src % 4)) return fail("float block sources must be 4-byte aligned");
+	if ((uintptr_t) d_dst % block_bytes(codec)) return fail("destination must be aligned to the block size");
 	if (codec == B200IC_BC6H) o.bc6h_signed = (format == B200IC_FMT_RGBA16F || format == B200IC_FMT_RGBA32F) ? 1 : o.bc6h_signed;
 	return dispatch(codec, img, o, d_dst, static_cast<cudaStream_t>(stream));
 }
 
-int b200ic_encode_host(int codec, const void *h_src, int format, uint32_t width, uint32_t height, uint64_t row_pitch_bytes,
-											 uint32_t slices, const b200ic_opts *opts, void *h_dst, b200ic_progress_fn progress, void *user) {
+// ---- host-buffer path --------------------------------------------------------------------------------------------
+// Progress is reported per finished block-row with the reference's own expression (e.g. src/amd_bc7_compressor.cpp:
+// 71-75: 100 * (y * blocksX) / (blocksX * blocksY) after row y of every slice), in order, from the thread that called
+// the encode when one device is used and serialised by a mutex when several are.
+struct HostJob {
+	int codec, format;
+	const uint8_t *src;
+	uint8_t *dst;
+	uint32_t width, height, slices, blocks_x, blocks_y, tb, bb;
+	uint64_t pitch;
+	const b200ic_opts *opts;
+	b200ic_progress_fn progress;
+	void *user;
+	bool src_pinned, dst_pinned;
+	std::atomic<int> cancelled{0};
+	std::mutex progress_mu;
+	std::string error; // first error of a worker thread
+	std::mutex error_mu;
+};
+
+static bool is_pinned(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void report_rows(HostJob &job, uint64_t g0, uint64_t g1) { // global rows [g0, g1): slice * blocks_y + block-row
+	if (!job.progress) return;
+	std::lock_guard<std::mutex> lock(job.progress_mu);
+	for (uint64_t g = g0; g < g1 && !job.cancelled.load(); g++) {
+		const size_t y = (size_t) (g % job.blocks_y);
+		const float pct = 100.f * (y * (size_t) job.blocks_x) / ((size_t) job.blocks_x * job.blocks_y);
+		if (job.progress(job.user, pct)) job.cancelled.store(1);
+	}
+}
+
+// Global rows [g0, g1) of the job on the CURRENT device through its context: chunks of whole block-rows (never across a
+// slice) pipelined over the stream ring -- stage (pageable sources: CPU copy into pinned memory), H2D, kernels, D2H,
+// un-stage.  The CPU copies of chunk c run while the GPU works on chunks c-1, c-2.
+static int encode_rows_on_device(DevCtx &cx, HostJob &job, uint64_t g0, uint64_t g1) {
+	if (g0 >= g1) return 0;
+	// ~8 MiB of input per chunk for the HBM-speed codecs; AMD BC7 spends ~100 ms on 32 MiB, so bigger chunks cost nothing
+	// and keep its per-mode launches long
+	const uint64_t chunk_bytes = job.codec == B200IC_BC7_AMD ? (32ull << 20) : (8ull << 20);
+	uint32_t rows_per_chunk = (uint32_t) std::max<uint64_t>(1, chunk_bytes / (job.pitch * 4));
+	rows_per_chunk = std::min(rows_per_chunk, job.blocks_y);
+	const size_t in_cap = (size_t) rows_per_chunk * 4 * job.pitch;
+	const size_t out_cap = (size_t) rows_per_chunk * job.blocks_x * job.bb;
+	constexpr int ring = DevCtx::kStreams;
+	struct Chunk {
+		uint64_t g0, g1;
+		uint8_t *hd;
+		size_t out_bytes;
+	};
+	std::vector<Chunk> chunks;
+	for (uint64_t g = g0; g < g1;) {
+		const uint64_t slice_end = (g / job.blocks_y + 1) * job.blocks_y;
+		const uint64_t e = std::min<uint64_t>(std::min<uint64_t>(g + rows_per_chunk, slice_end), g1);
+		chunks.push_back({g, e, nullptr, 0});
+		g = e;
+	}
+	for (int i = 0; i < ring && (size_t) i < chunks.size(); i++) {
+		if (cx.reserve(i, in_cap, out_cap)) return -1;
+		if (cx.reserve_pinned(i, job.src_pinned ? 0 : in_cap, job.dst_pinned ? 0 : out_cap)) return -1;
+	}
+	int rc = 0;
+	const size_t total = chunks.size();
+	for (size_t c = 0; c < total + ring && rc == 0; c++) {
+		if (c >= (size_t) ring) { // retire chunk c - ring before its slot is reused
+			Chunk &d = chunks[c - ring];
+			const int s = (int) ((c - ring) % ring);
+			cudaError_t e = cudaStreamSynchronize(cx.streams[s]);
+			if (e != cudaSuccess) { rc = fail("encode chunk", e); break; }
+			if (d.out_bytes) {
+				if (!job.dst_pinned) memcpy(d.hd, cx.p_out[s], d.out_bytes);
+				report_rows(job, d.g0, d.g1);
+			}
+		}
+		if (c >= total || job.cancelled.load()) continue;
+		Chunk &k = chunks[c];
+		const int s = (int) (c % ring);
+		const uint32_t slice = (uint32_t) (k.g0 / job.blocks_y);
+		const uint32_t by0 = (uint32_t) (k.g0 % job.blocks_y), by1 = by0 + (uint32_t) (k.g1 - k.g0);
+		const uint32_t y0 = by0 * 4, y1 = std::min(by1 * 4, job.height);
+		cudaStream_t st = cx.streams[s];
+		const uint8_t *hs = job.src + ((uint64_t) slice * job.height + y0) * job.pitch;
+		const size_t in_bytes = (size_t) (y1 - y0) * job.pitch;
+		if (!job.src_pinned) {
+			memcpy(cx.p_in[s], hs, in_bytes);
+			hs = static_cast<const uint8_t *>(cx.p_in[s]);
+		}
+		cudaError_t e = cudaMemcpyAsync(cx.d_in[s], hs, in_bytes, cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess) { rc = fail("H2D copy", e); break; }
+		if (job.codec == B200IC_BC7_AMD && c > 0) {
+			// one mode's kernels at a time on the SMs: chunk c's kernels start after chunk c-1's (the copies still overlap)
+			e = cudaStreamWaitEvent(st, cx.kdone[(c - 1) % ring], 0);
+			if (e != cudaSuccess) { rc = fail("stream wait", e); break; }
+		}
+		if (b200ic_encode_device(job.codec, cx.d_in[s], job.format, job.width, y1 - y0, job.pitch, 0, 1, job.opts, cx.d_out[s], st)) { rc = -1; break; }
+		if (job.codec == B200IC_BC7_AMD) cudaEventRecord(cx.kdone[s], st);
+		k.hd = job.dst + ((uint64_t) slice * job.blocks_y + by0) * job.blocks_x * job.bb;
+		k.out_bytes = (size_t) (by1 - by0) * job.blocks_x * job.bb;
+		e = cudaMemcpyAsync(job.dst_pinned ? (void *) k.hd : cx.p_out[s], cx.d_out[s], k.out_bytes, cudaMemcpyDeviceToHost, st);
+		if (e != cudaSuccess) { rc = fail("D2H copy", e); break; }
+	}
+	if (rc != 0 || job.cancelled.load())
+		for (int i = 0; i < ring; i++) cudaStreamSynchronize(cx.streams[i]);
+	return rc;
+}
+
+static int encode_host_impl(int codec, const void *h_src, int format, uint32_t width, uint32_t height, uint64_t row_pitch_bytes,
+														uint32_t slices, const b200ic_opts *opts, void *h_dst, b200ic_progress_fn progress, void *user, int n_devices) {
 	t_error.clear();
 	if (!h_src || !h_dst) return fail("null buffer");
 	if (width == 0 || height == 0 || slices == 0) return fail("empty image");
-	const uint32_t tb = texel_bytes(format), bb = block_bytes(codec);
-	if (tb == 0) return fail("unsupported source format");
-	if (bb == 0) return fail("unsupported codec");
+	HostJob job;
+	job.codec = codec;
+	job.format = format;
+	job.tb = texel_bytes(format);
+	job.bb = block_bytes(codec);
+	if (job.tb == 0) return fail("unsupported source format");
+	if (job.bb == 0) return fail("unsupported codec");
 	if (ensure_device()) return -1;
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (t_ctx.ensure(dev)) return -1;
-
-	const uint64_t pitch = row_pitch_bytes ? row_pitch_bytes : (uint64_t) width * tb;
-	const uint32_t blocks_x = (width + 3) / 4, blocks_y = (height + 3) / 4;
-	// chunk = whole block-rows, ~16 MiB of input each so copies overlap the kernels of neighbouring chunks.  AMD BC7
-	// spends seconds per 256 MiB (the copies are noise) and runs one launch per mode: big chunks keep launches of
-	// DIFFERENT modes from sharing the SMs (they evict each other's code, see launch_bc7amd)
-	const uint64_t chunk_bytes = codec == B200IC_BC7_AMD ? (256ull << 20) : (16ull << 20);
-	uint32_t rows_per_chunk = (uint32_t) (chunk_bytes / (pitch * 4));
-	if (rows_per_chunk < 1) rows_per_chunk = 1;
-	if (rows_per_chunk > blocks_y) rows_per_chunk = blocks_y;
-	const uint32_t chunks_per_slice = (blocks_y + rows_per_chunk - 1) / rows_per_chunk;
-	const uint64_t total_chunks = (uint64_t) chunks_per_slice * slices;
-	const size_t in_cap = (size_t) rows_per_chunk * 4 * pitch;
-	const size_t out_cap = (size_t) rows_per_chunk * blocks_x * bb;
-	const int ring = HostCtx::kStreams;
-	for (int i = 0; i < ring && (uint64_t) i < total_chunks; i++)
-		if (t_ctx.reserve(i, in_cap, out_cap)) return -1;
-
-	const uint8_t *src = static_cast<const uint8_t *>(h_src);
-	uint8_t *dst = static_cast<uint8_t *>(h_dst);
-	int rc = 0;
-	bool cancelled = false;
-	for (uint64_t c = 0; c < total_chunks + ring && rc == 0; c++) {
-		// retire chunk c-ring before its slot is reused (also drives the progress callback in order)
-		if (c >= (uint64_t) ring) {
-			const uint64_t done = c - ring;
-			cudaError_t e = cudaStreamSynchronize(t_ctx.streams[done % ring]);
-			if (e != cudaSuccess) { rc = fail("encode chunk", e); break; }
-			if (progress && !cancelled) {
-				const uint32_t cy = (uint32_t) (done % chunks_per_slice);
-				const float pct = 100.f * ((float) (done / chunks_per_slice) * blocks_y + (float) cy * rows_per_chunk) /
-													((float) blocks_y * slices);
-				if (progress(user, pct)) cancelled = true;
-			}
+	job.src = static_cast<const uint8_t *>(h_src);
+	job.dst = static_cast<uint8_t *>(h_dst);
+	job.width = width;
+	job.height = height;
+	job.slices = slices;
+	job.pitch = row_pitch_bytes ? row_pitch_bytes : (uint64_t) width * job.tb;
+	job.blocks_x = (width + 3) / 4;
+	job.blocks_y = (height + 3) / 4;
+	job.opts = opts;
+	job.progress = progress;
+	job.user = user;
+	job.src_pinned = is_pinned(h_src);
+	job.dst_pinned = is_pinned(h_dst);
+	const uint64_t rows = (uint64_t) job.blocks_y * slices;
+	int nd = n_devices;
+	const int visible = b200ic_device_count();
+	if (nd > visible) nd = visible;
+	if (nd > kMaxDevices) nd = kMaxDevices;
+	if ((uint64_t) nd > rows) nd = (int) rows;
+	if (nd <= 1) {
+		if (dev < 0 || dev >= kMaxDevices) return fail("device index out of range");
+		DevCtx &cx = g_ctx[dev];
+		std::lock_guard<std::mutex> lock(cx.mu);
+		if (cx.ensure(dev)) return -1;
+		const int rc = encode_rows_on_device(cx, job, 0, rows);
+		if (rc != 0) return rc;
+		return job.cancelled.load() ? 1 : 0;
+	}
+	// block-row shards over devices 0 .. nd-1, one host thread per device (src/amd_bc7_compressor.cpp:48-77 is the loop
+	// being split); no collective: every shard lands in its own range of h_dst
+	std::atomic<int> failed{0};
+	auto work = [&](int d) {
+		if (cudaSetDevice(d) != cudaSuccess || ensure_device()) {
+			std::lock_guard<std::mutex> lock(job.error_mu);
+			if (job.error.empty()) job.error = t_error.empty() ? "b200ic: cudaSetDevice failed" : t_error;
+			failed.store(1);
+			return;
 		}
-		if (c >= total_chunks || cancelled) continue;
-		const int s = (int) (c % ring);
-		const uint32_t slice = (uint32_t) (c / chunks_per_slice);
-		const uint32_t by0 = (uint32_t) (c % chunks_per_slice) * rows_per_chunk;
-		const uint32_t by1 = by0 + rows_per_chunk < blocks_y ? by0 + rows_per_chunk : blocks_y;
-		const uint32_t y0 = by0 * 4, y1 = by1 * 4 < height ? by1 * 4 : height;
-		cudaStream_t st = t_ctx.streams[s];
-		const uint8_t *hs = src + ((uint64_t) slice * height + y0) * pitch;
-		cudaError_t e = cudaMemcpyAsync(t_ctx.d_in[s], hs, (size_t) (y1 - y0) * pitch, cudaMemcpyHostToDevice, st);
-		if (e != cudaSuccess) { rc = fail("H2D copy", e); break; }
-		if (b200ic_encode_device(codec, t_ctx.d_in[s], format, width, y1 - y0, pitch, 0, 1, opts, t_ctx.d_out[s], st)) { rc = -1; break; }
-		uint8_t *hd = dst + ((uint64_t) slice * blocks_y + by0) * blocks_x * bb;
-		e = cudaMemcpyAsync(hd, t_ctx.d_out[s], (size_t) (by1 - by0) * blocks_x * bb, cudaMemcpyDeviceToHost, st);
-		if (e != cudaSuccess) { rc = fail("D2H copy", e); break; }
+		DevCtx &cx = g_ctx[d];
+		std::lock_guard<std::mutex> lock(cx.mu);
+		const uint64_t a = rows * (uint64_t) d / nd, b = rows * (uint64_t) (d + 1) / nd;
+		if (cx.ensure(d) || encode_rows_on_device(cx, job, a, b)) {
+			std::lock_guard<std::mutex> lock2(job.error_mu);
+			if (job.error.empty()) job.error = t_error;
+			failed.store(1);
+		}
+	};
+	std::vector<std::thread> pool;
+	for (int d = 0; d < nd; d++) pool.emplace_back(work, d);
+	for (auto &t : pool) t.join();
+	cudaSetDevice(dev);
+	if (failed.load()) {
+		t_error = job.error;
+		return -1;
 	}
-	if (rc != 0 || cancelled) {
-		for (int i = 0; i < ring; i++) cudaStreamSynchronize(t_ctx.streams[i]);
-		return rc != 0 ? rc : 1;
+	return job.cancelled.load() ? 1 : 0;
+}
+
+int b200ic_encode_host(int codec, const void *h_src, int format, uint32_t width, uint32_t height, uint64_t row_pitch_bytes,
+											 uint32_t slices, const b200ic_opts *opts, void *h_dst, b200ic_progress_fn progress, void *user) {
+	return encode_host_impl(codec, h_src, format, width, height, row_pitch_bytes, slices, opts, h_dst, progress, user, 1);
+}
+
+int b200ic_encode_host_sharded(int codec, const void *h_src, int format, uint32_t width, uint32_t height, uint64_t row_pitch_bytes,
+															 uint32_t slices, const b200ic_opts *opts, void *h_dst, b200ic_progress_fn progress, void *user, int n_devices) {
+	return encode_host_impl(codec, h_src, format, width, height, row_pitch_bytes, slices, opts, h_dst, progress, user,
+													n_devices <= 0 ? b200ic_device_count() : n_devices);
+}
+
+static std::atomic<int> g_shim_devices{-1}; // -1: not set (environment / all visible)
+void b200ic_set_devices(int n) { g_shim_devices.store(n < 0 ? 0 : n); }
+int b200ic_get_devices(void) {
+	int n = g_shim_devices.load();
+	if (n < 0) {
+		const char *e = getenv("B200IC_DEVICES"); // read once
+		n = e ? atoi(e) : 0;
+		if (n < 0) n = 0;
+		g_shim_devices.store(n);
 	}
-	return 0;
+	const int visible = b200ic_device_count();
+	if (n == 0 || n > visible) n = visible;
+	return n < 1 ? 1 : n;
 }
 
 int b200ic_encode_blocks(int codec, const void *h_blocks, int format, uint64_t nblocks, const b200ic_opts *opts, void *h_dst) {
@@ -359,12 +554,15 @@ int b200ic_encode_blocks(int codec, const void *h_blocks, int format, uint64_t n
 	if (ensure_device()) return -1;
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (t_ctx.ensure(dev)) return -1;
-	if (t_ctx.reserve(0, (size_t) nblocks * fb, (size_t) nblocks * bb)) return -1;
-	cudaStream_t st = t_ctx.streams[0];
-	B200IC_CUDA(cudaMemcpyAsync(t_ctx.d_in[0], h_blocks, (size_t) nblocks * fb, cudaMemcpyHostToDevice, st), "H2D copy");
-	if (b200ic_encode_device(codec, t_ctx.d_in[0], format, (uint32_t) nblocks, 1, 0, 0, 1, opts, t_ctx.d_out[0], st)) return -1;
-	B200IC_CUDA(cudaMemcpyAsync(h_dst, t_ctx.d_out[0], (size_t) nblocks * bb, cudaMemcpyDeviceToHost, st), "D2H copy");
+	if (dev < 0 || dev >= kMaxDevices) return fail("device index out of range");
+	DevCtx &cx = g_ctx[dev];
+	std::lock_guard<std::mutex> lock(cx.mu);
+	if (cx.ensure(dev)) return -1;
+	if (cx.reserve(0, (size_t) nblocks * fb, (size_t) nblocks * bb)) return -1;
+	cudaStream_t st = cx.streams[0];
+	B200IC_CUDA(cudaMemcpyAsync(cx.d_in[0], h_blocks, (size_t) nblocks * fb, cudaMemcpyHostToDevice, st), "H2D copy");
+	if (b200ic_encode_device(codec, cx.d_in[0], format, (uint32_t) nblocks, 1, 0, 0, 1, opts, cx.d_out[0], st)) return -1;
+	B200IC_CUDA(cudaMemcpyAsync(h_dst, cx.d_out[0], (size_t) nblocks * bb, cudaMemcpyDeviceToHost, st), "D2H copy");
 	B200IC_CUDA(cudaStreamSynchronize(st), "encode blocks");
 	return 0;
 }
@@ -427,13 +625,16 @@ int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint6
 	if (ensure_device()) return -1;
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (t_ctx.ensure(dev)) return -1;
+	if (dev < 0 || dev >= kMaxDevices) return fail("device index out of range");
+	DevCtx &cx = g_ctx[dev];
+	std::lock_guard<std::mutex> lock(cx.mu);
+	if (cx.ensure(dev)) return -1;
 	const uint64_t count = shards ? n_shards : n_images;
 	if (count == 0) return 0;
 	cudaStream_t user = static_cast<cudaStream_t>(stream);
-	const int ring = HostCtx::kStreams;
-	B200IC_CUDA(cudaEventRecord(t_ctx.fork, user), "fork");
-	for (int i = 0; i < ring; i++) B200IC_CUDA(cudaStreamWaitEvent(t_ctx.streams[i], t_ctx.fork, 0), "fork");
+	const int ring = DevCtx::kStreams;
+	B200IC_CUDA(cudaEventRecord(cx.fork, user), "fork");
+	for (int i = 0; i < ring; i++) B200IC_CUDA(cudaStreamWaitEvent(cx.streams[i], cx.fork, 0), "fork");
 	int rc = 0;
 	for (uint64_t k = 0; k < count && rc == 0; k++) {
 		b200ic_shard sh;
@@ -452,11 +653,11 @@ int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint6
 		const uint8_t *src = static_cast<const uint8_t *>(im.src) + (uint64_t) y0 * pitch;
 		uint8_t *dst = static_cast<uint8_t *>(im.dst) + (uint64_t) r0 * blocks_x * bb;
 		// big shards fill the GPU on their own and go to the caller's order on stream 0; small ones (low mips) overlap
-		rc = b200ic_encode_device(codec, src, im.format, im.width, y1 - y0, pitch, 0, 1, opts, dst, t_ctx.streams[k % ring]);
+		rc = b200ic_encode_device(codec, src, im.format, im.width, y1 - y0, pitch, 0, 1, opts, dst, cx.streams[k % ring]);
 	}
 	for (int i = 0; i < ring; i++) {
-		cudaEventRecord(t_ctx.join[i], t_ctx.streams[i]);
-		cudaStreamWaitEvent(user, t_ctx.join[i], 0);
+		cudaEventRecord(cx.join[i], cx.streams[i]);
+		cudaStreamWaitEvent(user, cx.join[i], 0);
 	}
 	return rc;
 }

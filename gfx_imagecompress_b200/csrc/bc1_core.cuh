@@ -416,6 +416,14 @@ B1_HDN float compress(const float in[64], int np, bool use_alpha, float thr, int
 	return err;
 }
 
+// One texel of Image_CompressAMDExplictAlphaSingleModeBlock (src/amd_bcx_helpers.cpp:107-123): 8 -> 4 bits with the
+// reference's rounding (+7 or +8 minus the high nibble)
+B1_HD uint32_t explicit_alpha4(float a) {
+	uint8_t c = (uint8_t) (a * 255.0f);
+	c = (uint8_t) ((c + ((c >> 4) < 0x8 ? 7 : 8) - (c >> 4)) >> 4);
+	return c > 0xf ? 0xfu : (uint32_t) c;
+}
+
 // The two halves of Image_CompressAMDBC1Block for a lane pair: `which` 0 = the 3-point fit, 1 = the 4-point fit (the
 // reference skips the latter when the former is exact; its result cannot win then, e3 = 0 <= e4, so running it anyway
 // changes nothing).  pack_fit() is the selection and packing (:89-104) from the two errors.

@@ -36,6 +36,7 @@ struct Bc45Params {
 	uint64_t n_items;  // channel blocks
 	int32_t channels;  // 1 (BC4) or 2 (BC5)
 	int32_t first_channel;
+	int32_t dst_stride; // bytes from one channel block to the next (8; 16 when the blocks are the alpha halves of BC3)
 };
 
 // RmpSrch1 (src/amd_bcx_body.cpp:1510-1548) without the early-out; ur[i] = (unique value, repeat count)
@@ -279,17 +280,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) bc45_kernel(const Bc45Param
 		w0 |= __shfl_xor_sync(FULL, w0, d);
 		w1 |= __shfl_xor_sync(FULL, w1, d);
 	}
-	if (valid && l16 == 0) *reinterpret_cast<uint2 *>(p.dst + item * 8) = make_uint2(w0, w1);
+	if (valid && l16 == 0) *reinterpret_cast<uint2 *>(p.dst + item * (uint64_t) p.dst_stride) = make_uint2(w0, w1);
 }
 
 } // namespace
 
-cudaError_t launch_bc45(const SrcImage &img, int channels, int first_channel, void *dst, cudaStream_t stream) {
+cudaError_t launch_bc45(const SrcImage &img, int channels, int first_channel, void *dst, cudaStream_t stream, int dst_stride) {
 	Bc45Params p;
 	p.img = img;
 	p.dst = static_cast<uint8_t *>(dst);
 	p.channels = channels;
 	p.first_channel = first_channel;
+	p.dst_stride = dst_stride;
 	p.n_items = (uint64_t) img.blocks_x * img.blocks_y * img.slices * (uint64_t) channels;
 	if (p.n_items == 0) return cudaSuccess;
 	const uint64_t per_cta = (uint64_t) kWarpsPerCta * 2;

@@ -24,6 +24,8 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "bc7amd_block.cuh"
+#include <mutex>
+#include <vector>
 
 namespace b200ic {
 
@@ -37,6 +39,7 @@ constexpr int kItemBatch = 160; // window phase: work items evaluated between tw
 constexpr uint32_t kChunkBlocks = 1u << 19; // blocks per pass over the phase kernels (bounds the scratch: 584 B per block)
 
 uint32_t *g_sp_table_host[16] = {};
+int g_serial_modes = 0x40; // modes run by the thread-per-block kernel (debug builds: b200ic_amd_serial_modes)
 
 // Quantise-phase task order: (partition, subset) pairs of each partition table sorted by subset size (descending),
 // so that the 32 lanes of one round run optQuantAnD problems of (nearly) the same size. Pure scheduling data.
@@ -77,6 +80,7 @@ struct ShakeOut {
 // vector | scalar) part of a dual-index mode
 struct Task {
 	uint32_t d[16];     // packed texels
+	uint32_t plane[16]; // the same, channel-planar (window_planes_u8; filled by the window kernel only)
 	uint64_t idx_q;     // quantiser indices
 	uint64_t cur;       // collapsed indices of the running pass
 	uint64_t best_idx;  // index_io of the reference's ep_shaker_d
@@ -196,6 +200,51 @@ __device__ __forceinline__ void build_single_index_task(Task &t, const uint32_t 
 	t.item_base = t.item_count = 0;
 }
 
+// Task table of a dual-index mode (4, 5): lane = 2 * (rotation * selections + index selection) + (0 vector | 1 scalar).
+// The scalar channel is searched as a 3-vector with the channel replicated (src/amd_bc7_body.cpp:1094-1096).
+struct DualShape {
+	int nsel, combos, ntasks;
+};
+__device__ __forceinline__ DualShape dual_shape(const ModeInfo &mi) {
+	DualShape s;
+	s.nsel = 1 << mi.index_mode_bits;
+	s.combos = (1 << mi.rotation_bits) * s.nsel;
+	s.ntasks = s.combos * 2;
+	return s;
+}
+__device__ __forceinline__ int dual_index_bits(const ModeInfo &mi, int isel, int which) {
+	return which == 0 ? (isel ? mi.index_bits1 : mi.index_bits0) : (isel ? mi.index_bits0 : mi.index_bits1);
+}
+__device__ __forceinline__ void build_dual_index_task(Task &t, const uint32_t *px, const ModeInfo &mi, int lane, uint64_t idx_q) {
+	const DualShape ds = dual_shape(mi);
+	const int combo = lane >> 1, which = lane & 1;
+	const int rot = combo / ds.nsel, isel = combo - rot * ds.nsel;
+	const int c0 = rotation_channel(rot, 0), c1 = rotation_channel(rot, 1), c2 = rotation_channel(rot, 2), c3 = rotation_channel(rot, 3);
+	bool same = true;
+	for (int i = 0; i < 16; i++) {
+		const uint32_t v = px[i];
+		uint32_t w;
+		if (which == 0) w = ((v >> (8 * c1)) & 255u) | (((v >> (8 * c2)) & 255u) << 8) | (((v >> (8 * c3)) & 255u) << 16);
+		else w = ((v >> (8 * c0)) & 255u) * 0x010101u;
+		t.d[i] = w;
+		same = same && (w == t.d[0]);
+	}
+	const int cb = which == 0 ? mi.vector_bits / 3 : mi.scalar_bits;
+	t.idx_q = idx_q;
+	t.n = 16;
+	t.clog = (uint8_t) dual_index_bits(mi, isel, which);
+	t.bits = (uint8_t) cb;
+	t.type = CART;
+	t.all_same = same ? 1 : 0;
+	t.dim = 3;
+	t.w_bits_total = (uint8_t) (6 * cb);
+	t.w_size = 6;
+	t.w_index = idx_q;
+	t.w_active = 1;
+	t.done = 0;
+	t.item_base = t.item_count = 0;
+}
+
 // Start (or restart) a pass of ep_shaker_d for one task: collapse the indices, handle the single-index case.
 __device__ __noinline__ void cube_begin_pass(const Tables &T, Task &t, uint64_t from) {
 	int index[kMaxEntries];
@@ -270,7 +319,7 @@ struct QuantScratch {
 	real qs[2][16][32];   // the two lane-strided FP64 work arrays of QuantIO (element k of lane l at [k][l])
 };
 
-__global__ void __launch_bounds__(kWarps * 32, 3) amd_quant_kernel(const AmdParams p) {
+__global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	QuantScratch *scratch = reinterpret_cast<QuantScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -320,10 +369,32 @@ __global__ void __launch_bounds__(kWarps * 32, 3) amd_quant_kernel(const AmdPara
 		return;
 	}
 	const ModeInfo mi = mode_info(mode);
+	AMD_T0();
+	if (mi.alpha == 2) { // dual-index modes: one 16-texel problem per (rotation, index selection, vector | scalar)
+		const DualShape ds = dual_shape(mi);
+		if ((int) lane < ds.ntasks) {
+			const int combo = (int) lane >> 1, which = (int) lane & 1;
+			const int rot = combo / ds.nsel, isel = combo - rot * ds.nsel;
+			const uint32_t c0 = (uint32_t) rotation_channel(rot, 0), c1 = (uint32_t) rotation_channel(rot, 1),
+										 c2 = (uint32_t) rotation_channel(rot, 2), c3 = (uint32_t) rotation_channel(rot, 3);
+			QuantIO io;
+			io.px = &ws.B.pxc[0][0];
+			io.texels = 0xFEDCBA9876543210ull;
+			io.chan = which == 0 ? (c1 | (c2 << 2) | (c3 << 4)) : (c0 | (c0 << 2) | (c0 << 4));
+			io.proj = &ws.qs[0][0][lane];
+			io.dev = &ws.qs[1][0][lane];
+			io.stride = 32;
+			uint64_t qpacked = 0;
+			quantise_subset(io, 16, 1 << dual_index_bits(mi, isel, which), 3, qpacked);
+			p.s.q_idx[(size_t) block * kMaxTasks + lane] = qpacked;
+		}
+		if (lane == 0) p.s.q_top[(size_t) block * 8] = 0;
+		AMD_T(0);
+		return;
+	}
 	const ShakeParams sp = single_index_shake_params(mode);
 	const int nparts = 1 << mi.partition_bits, subsets = mi.subsets;
 	const uint8_t *qorder = quantise_order(subsets, nparts);
-	AMD_T0();
 	QuantIO io;
 	io.px = &ws.B.pxc[0][0];
 	io.chan = 0xE4u;
@@ -420,7 +491,7 @@ __device__ __forceinline__ void cube_item_corners(const CubeScratch &ws, const u
 }
 
 // ep_shaker_d for all tasks of the warp. On return task[i].err_o / best_idx hold its result.
-__device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, int ntasks, unsigned lane) {
+__device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, unsigned lane) {
 	if ((int) lane < ntasks) {
 		Task &t = ws.task[lane];
 		t.err_o = A7_HUGE;
@@ -493,9 +564,9 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, int
 					const uint32_t *ep = ws.item_ep[j];
 					uint32_t *tw = reinterpret_cast<uint32_t *>(ws.tab);
 					if (clog == 2) {
-						for (int id = (int) lane; id < (12 << nlb); id += 32) tw[2 * id] = cube_tab_word<2>(ep, bcc, id);
+						for (int id = (int) lane; id < (12 << nlb); id += 32) tw[2 * id] = cube_tab_word_lut<2>(lut2, ep, bcc, id);
 					} else {
-						for (int id = (int) lane; id < (24 << nlb); id += 32) tw[id] = cube_tab_word<3>(ep, bcc, id);
+						for (int id = (int) lane; id < (24 << nlb); id += 32) tw[id] = cube_tab_word_lut<3>(lut3, ep, bcc, id);
 					}
 				}
 				__syncwarp();
@@ -532,32 +603,47 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, int
 	}
 }
 
-__global__ void __launch_bounds__(kWarps * 32) amd_cube_kernel(const AmdParams p) {
+// Persistent: the grid is sized to the SMs, every warp strides over the blocks of the chunk; the two difference tables
+// of the ramps (6 KB, bc7amd_int.cuh) are built once per CTA.
+constexpr int kCubeCtasPerSm = 5;
+constexpr int kWaves = 8; // CTAs per resident slot: the hardware scheduler evens out the data-dependent block times, the tables amortise over ~100 blocks
+__global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(const AmdParams p) {
 	__shared__ CubeScratch scratch[kWarps];
+	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
+	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWarps * 32);
+	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWarps * 32);
+	__syncthreads();
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t block = blockIdx.x * kWarps + warp;
-	if (block >= p.n_blocks) return; // whole warp
-	if (p.s.q_top[(size_t) block * 8] == 0xffu) return; // whole warp: mode not searched for this block
 	CubeScratch &ws = scratch[warp];
 	const Tables T{p.sp};
-	const BlockCoord bc = block_coord(p, block);
-	if (lane < 16) ws.px[lane] = fetch_rgba_u8(p.img, bc, (int) lane);
-	__syncwarp();
 	const ModeInfo mi = mode_info(p.mode);
 	const ShakeParams sp = single_index_shake_params(p.mode);
-	const int subsets = mi.subsets, ntasks = 8 * subsets;
-	AMD_T0();
-	if ((int) lane < ntasks) {
-		const int a = (int) lane / subsets, s = (int) lane - a * subsets;
-		build_single_index_task(ws.task[lane], ws.px, subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, p.s.q_idx[(size_t) block * kMaxTasks + lane]);
+	const int subsets = mi.subsets, ntasks = mi.alpha == 2 ? dual_shape(mi).ntasks : 8 * subsets;
+#pragma unroll 1
+	for (uint32_t block = blockIdx.x * kWarps + warp; block < p.n_blocks; block += gridDim.x * kWarps) {
+		if (p.s.q_top[(size_t) block * 8] == 0xffu) continue; // whole warp: mode not searched for this block
+		const BlockCoord bc = block_coord(p, block);
+		__syncwarp();
+		if (lane < 16) ws.px[lane] = fetch_rgba_u8(p.img, bc, (int) lane);
+		__syncwarp();
+		AMD_T0();
+		if ((int) lane < ntasks) {
+			const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + lane];
+			if (mi.alpha == 2) {
+				build_dual_index_task(ws.task[lane], ws.px, mi, (int) lane, idx_q);
+			} else {
+				const int a = (int) lane / subsets, s = (int) lane - a * subsets;
+				build_single_index_task(ws.task[lane], ws.px, subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, idx_q);
+			}
+		}
+		__syncwarp();
+		cube_phase(T, ws, lut2, lut3, ntasks, lane);
+		if ((int) lane < ntasks) {
+			p.s.c_idx[(size_t) block * kMaxTasks + lane] = ws.task[lane].best_idx;
+			p.s.c_err[(size_t) block * kMaxTasks + lane] = ws.task[lane].err_o;
+		}
+		AMD_T(2);
 	}
-	__syncwarp();
-	cube_phase(T, ws, ntasks, lane);
-	if ((int) lane < ntasks) {
-		p.s.c_idx[(size_t) block * kMaxTasks + lane] = ws.task[lane].best_idx;
-		p.s.c_err[(size_t) block * kMaxTasks + lane] = ws.task[lane].err_o;
-	}
-	AMD_T(2);
 }
 
 // =====================================================================================================================
@@ -601,7 +687,7 @@ __device__ __noinline__ void window_begin_round(const Tables &T, Task &t) {
 }
 
 // ep_shaker_2_d for the tasks with w_active set, starting from task.w_index. Results in w_err_o / w_best_idx / w_best_ep.
-__device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, int ntasks, unsigned lane) {
+__device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, unsigned lane) {
 	if ((int) lane < ntasks) {
 		Task &t = ws.task[lane];
 		t.done = t.w_active ? 0 : 1;
@@ -634,8 +720,8 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, in
 				qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
 				uint64_t epo;
 				uint32_t err;
-				if (t.clog == 2) err = window_item_u8<2>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
-				else if (t.clog == 3) err = window_item_u8<3>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
+				if (t.clog == 2) err = window_item_lut_u8<2>(lut2, t.d, t.plane, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
+				else if (t.clog == 3) err = window_item_lut_u8<3>(lut3, t.d, t.plane, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
 				else err = window_item_u8<4>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
 				ws.item_key[it - b0] = ((uint64_t) err << 8) | (uint64_t) (255 - qp); // `<=`: the LAST minimum wins
 				ws.item_idx[it - b0] = epo;
@@ -682,12 +768,9 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, in
 	}
 }
 
-__global__ void __launch_bounds__(kWarps * 32) amd_window_kernel(const AmdParams p) {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	WindowScratch *scratch = reinterpret_cast<WindowScratch *>(smem_raw);
-	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-	const uint32_t block = blockIdx.x * kWarps + warp;
-	if (block >= p.n_blocks) return; // whole warp
+// One block of the window kernel
+__device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3,
+																						 uint32_t block, unsigned lane) {
 	const BlockCoord bc = block_coord(p, block);
 	if (p.s.q_top[(size_t) block * 8] == 0xffu) { // whole warp: mode not searched for this block
 		if (p.first && lane == 0) {
@@ -696,29 +779,76 @@ __global__ void __launch_bounds__(kWarps * 32) amd_window_kernel(const AmdParams
 		}
 		return;
 	}
-	WindowScratch &ws = scratch[warp];
-	const Tables T{p.sp};
+	__syncwarp();
 	if (lane < 16) ws.px[lane] = fetch_rgba_u8(p.img, bc, (int) lane);
 	if (lane < 8) ws.top[lane] = p.s.q_top[(size_t) block * 8 + lane];
 	__syncwarp();
 	const int mode = p.mode;
 	const ModeInfo mi = mode_info(mode);
 	const ShakeParams sp = single_index_shake_params(mode);
-	const int subsets = mi.subsets, ntasks = 8 * subsets;
-	const bool cube = sp.dim == 3;
+	const bool dual = mi.alpha == 2;
+	const int subsets = mi.subsets, ntasks = dual ? dual_shape(mi).ntasks : 8 * subsets;
+	const bool cube = dual || sp.dim == 3;
 	AMD_T0();
 	if ((int) lane < ntasks) {
 		const int a = (int) lane / subsets, s = (int) lane - a * subsets;
 		Task &t = ws.task[lane];
-		build_single_index_task(t, ws.px, subsets, ws.top[a], s, sp, p.s.q_idx[(size_t) block * kMaxTasks + lane]);
+		const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + lane];
+		if (dual) build_dual_index_task(t, ws.px, mi, (int) lane, idx_q);
+		else build_single_index_task(t, ws.px, subsets, ws.top[a], s, sp, idx_q);
 		if (cube) {
 			t.best_idx = p.s.c_idx[(size_t) block * kMaxTasks + lane];
 			t.err_o = p.s.c_err[(size_t) block * kMaxTasks + lane];
 		}
+		if (dual) t.w_index = t.best_idx; // ep_shaker_2_d runs on ep_shaker_d's indices only (src/amd_bc7_body.cpp:1120-1160)
+		window_planes_u8(t.d, t.n, t.plane);
 	}
 	__syncwarp();
+	if (dual) {
+		window_phase(T, ws, lut2, lut3, ntasks, lane);
+		AMD_T(3);
+		if ((int) lane < ntasks) {
+			const Task &t = ws.task[lane];
+			ShakeOut o;
+			o.err = t.w_err_o;
+			o.idx = t.w_best_idx;
+			o.ep[0] = (uint32_t) t.w_best_ep;
+			o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
+			ws.so[lane] = o;
+		}
+		__syncwarp();
+		if (lane == 0) {
+			const DualShape ds = dual_shape(mi);
+			real be = A7_HUGE;
+			int bcm = 0;
+			for (int c = 0; c < ds.combos; c++) {
+				real e = 0;
+				e += ws.so[2 * c].err;
+				e += ws.so[2 * c + 1].err / 3.;
+				if (e < be) { be = e; bcm = c; }
+			}
+			const real carried = p.first ? A7_HUGE : p.best_err[bc.gblock];
+			if (p.first || be < carried) {
+				int epp[2][2][4], idxp[2][16];
+				for (int w = 0; w < 2; w++) {
+					const ShakeOut &o = ws.so[2 * bcm + w];
+					for (int k = 0; k < 4; k++) {
+						epp[w][0][k] = (int) ((o.ep[0] >> (8 * k)) & 255u);
+						epp[w][1][k] = (int) ((o.ep[1] >> (8 * k)) & 255u);
+					}
+					for (int i = 0; i < 16; i++) idxp[w][i] = (int) ((o.idx >> (4 * i)) & 15u);
+				}
+				uint64_t blk[2];
+				pack_dual_index(mode, bcm % ds.nsel, bcm / ds.nsel, epp, idxp, blk);
+				p.dst[bc.gblock] = make_uint4((uint32_t) blk[0], (uint32_t) (blk[0] >> 32), (uint32_t) blk[1], (uint32_t) (blk[1] >> 32));
+				p.best_err[bc.gblock] = be;
+			}
+		}
+		AMD_T(5);
+		return;
+	}
 	// shake_subset (:709-805): ep_shaker_2_d on the quantiser's indices and, where ep_shaker_d won, again on its indices
-	window_phase(T, ws, ntasks, lane);
+	window_phase(T, ws, lut2, lut3, ntasks, lane);
 	AMD_T(3);
 	if (cube) {
 		if ((int) lane < ntasks) {
@@ -727,7 +857,7 @@ __global__ void __launch_bounds__(kWarps * 32) amd_window_kernel(const AmdParams
 			t.w_index = t.best_idx;
 		}
 		__syncwarp();
-		window_phase(T, ws, ntasks, lane);
+		window_phase(T, ws, lut2, lut3, ntasks, lane);
 		AMD_T(4);
 	}
 	if ((int) lane < ntasks) {
@@ -767,6 +897,23 @@ __global__ void __launch_bounds__(kWarps * 32) amd_window_kernel(const AmdParams
 		}
 	}
 	AMD_T(5);
+}
+
+
+constexpr int kWindowCtasPerSm = 4;
+__global__ void __launch_bounds__(kWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	WindowScratch *scratch = reinterpret_cast<WindowScratch *>(smem_raw);
+	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
+	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWarps * 32);
+	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWarps * 32);
+	__syncthreads();
+	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+	WindowScratch &ws = scratch[warp];
+	const Tables T{p.sp};
+#pragma unroll 1
+	for (uint32_t block = blockIdx.x * kWarps + warp; block < p.n_blocks; block += gridDim.x * kWarps)
+		window_block(p, ws, T, lut2, lut3, block, lane);
 }
 
 // =====================================================================================================================
@@ -1014,6 +1161,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) bc7amd_float_kernel(const AmdP
 } // namespace
 
 #ifdef B200IC_AMD_TIMING
+extern "C" __attribute__((visibility("default"))) void b200ic_amd_serial_modes(int mask) { g_serial_modes = (mask & 0x30) | 0x40; }
 extern "C" __attribute__((visibility("default"))) int b200ic_amd_timing(unsigned long long *out, int reset) {
 	cudaDeviceSynchronize();
 	if (out) cudaMemcpyFromSymbol(out, g_amd_timing, sizeof(g_amd_timing));
@@ -1024,6 +1172,58 @@ extern "C" __attribute__((visibility("default"))) int b200ic_amd_timing(unsigned
 	return 0;
 }
 #endif
+
+// ---- per-kernel timing for bench.py's roofline (b200ic_profile / b200ic_profile_read, include/b200ic.h): with profiling
+// on, every kernel of the AMD BC7 pipeline is bracketed by CUDA events on the launching stream
+namespace {
+struct ProfEvent {
+	int mode, kind; // kind: 0 quantise, 1 cube, 2 window, 3 thread-per-block / float kernel
+	cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+std::vector<ProfEvent> g_prof_events;
+bool g_prof_on = false;
+struct ProfScope {
+	cudaStream_t st;
+	ProfEvent ev;
+	bool on;
+	ProfScope(cudaStream_t s, int mode, int kind) : st(s), on(g_prof_on) {
+		if (!on) return;
+		ev.mode = mode;
+		ev.kind = kind;
+		cudaEventCreate(&ev.a);
+		cudaEventCreate(&ev.b);
+		cudaEventRecord(ev.a, st);
+	}
+	~ProfScope() {
+		if (!on) return;
+		cudaEventRecord(ev.b, st);
+		std::lock_guard<std::mutex> lock(g_prof_mu);
+		g_prof_events.push_back(ev);
+	}
+};
+} // namespace
+extern "C" __attribute__((visibility("default"))) void b200ic_profile(int enable) { g_prof_on = enable != 0; }
+extern "C" __attribute__((visibility("default"))) int b200ic_profile_read(double *ms, uint64_t *launches) {
+	std::lock_guard<std::mutex> lock(g_prof_mu);
+	for (int i = 0; i < 32; i++) {
+		if (ms) ms[i] = 0;
+		if (launches) launches[i] = 0;
+	}
+	int n = 0;
+	for (ProfEvent &e : g_prof_events) {
+		float t = 0;
+		if (cudaEventSynchronize(e.b) == cudaSuccess && cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) {
+			if (ms) ms[e.mode * 4 + e.kind] += (double) t;
+			if (launches) launches[e.mode * 4 + e.kind]++;
+			n++;
+		}
+		cudaEventDestroy(e.a);
+		cudaEventDestroy(e.b);
+	}
+	g_prof_events.clear();
+	return n;
+}
 
 cudaError_t init_bc7amd_tables() {
 	int dev = 0;
@@ -1074,6 +1274,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	if (dev < 0 || dev >= 16 || !g_sp_table_host[dev]) return cudaErrorInitializationError;
 	const uint64_t total_blocks = (uint64_t) img.blocks_x * img.blocks_y * img.slices;
 	if (total_blocks == 0) return cudaSuccess;
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	AmdParams p;
 	p.img = img;
 	p.dst = static_cast<uint4 *>(dst);
@@ -1107,6 +1309,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 		p.block0 = b0;
 		p.n_blocks = (uint32_t) (total_blocks - b0 < chunk ? total_blocks - b0 : chunk);
 		const unsigned warp_grid = (p.n_blocks + kWarps - 1) / kWarps;
+		const unsigned window_grid = warp_grid < (unsigned) (sms * kWindowCtasPerSm * kWaves) ? warp_grid : (unsigned) (sms * kWindowCtasPerSm * kWaves);
+		const unsigned cube_grid = warp_grid < (unsigned) (sms * kCubeCtasPerSm * kWaves) ? warp_grid : (unsigned) (sms * kCubeCtasPerSm * kWaves);
 		int passes = 0;
 		for (int vi = 0; vi < 8; vi++) {
 			const int mode = mode_visit_order(vi);
@@ -1114,6 +1318,7 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 				if (vi) break;
 				p.launch_modes = 0xFFu;
 				p.first = 1;
+				ProfScope ps(stream, 0, 3);
 				bc7amd_float_kernel<<<warp_grid, kWarps * 32, kWarps * sizeof(FloatScratch), stream>>>(p);
 				launches++;
 				continue;
@@ -1122,13 +1327,23 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 			p.launch_modes = 1u << mode;
 			p.mode = mode;
 			p.first = passes == 0;
-			if (mode >= 4 && mode <= 6) {
+			if (mode == 6 || ((g_serial_modes >> mode) & 1)) {
+				ProfScope ps(stream, mode, 3);
 				bc7amd_serial_kernel<<<(p.n_blocks + 127) / 128, 128, 0, stream>>>(p, mode);
 				launches++;
 			} else {
-				amd_quant_kernel<<<warp_grid, kWarps * 32, kWarps * sizeof(QuantScratch), stream>>>(p);
-				if (mode != 7) amd_cube_kernel<<<warp_grid, kWarps * 32, 0, stream>>>(p);
-				amd_window_kernel<<<warp_grid, kWarps * 32, kWarps * sizeof(WindowScratch), stream>>>(p);
+				{
+					ProfScope ps(stream, mode, 0);
+					amd_quant_kernel<<<warp_grid, kWarps * 32, kWarps * sizeof(QuantScratch), stream>>>(p);
+				}
+				if (mode != 7) {
+					ProfScope ps(stream, mode, 1);
+					amd_cube_kernel<<<cube_grid, kWarps * 32, 0, stream>>>(p);
+				}
+				{
+					ProfScope ps(stream, mode, 2);
+					amd_window_kernel<<<window_grid, kWarps * 32, kWarps * sizeof(WindowScratch), stream>>>(p);
+				}
 				launches += mode != 7 ? 3 : 2;
 			}
 			passes++;

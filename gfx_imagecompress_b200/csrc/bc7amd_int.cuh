@@ -641,13 +641,13 @@ A7_HD void cube_lane_corners(const uint64_t *tab, const uint32_t (&d)[16], int n
 			for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<0>(pzy[c], tx, c);
 			uint32_t err = 0;
 #pragma unroll
-			for (int t = 0; t < 16; t++)
-				if (t < n) {
-					uint32_t m = sq_dist4(pal[0], d[t]);
+			for (int t = 0; t < 16; t++) {
+				if (t >= n) break; // n is warp-uniform on the GPU: one branch per texel, none after the last
+				uint32_t m = sq_dist4(pal[0], d[t]);
 #pragma unroll
-					for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], d[t]));
-					err += m;
-				}
+				for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], d[t]));
+				err += m;
+			}
 			const uint32_t key = (err << 8) | (gzy ^ (uint32_t) gray_position(x));
 			if (key < best_key) {
 				best_key = key;
@@ -663,6 +663,79 @@ template <int CLOG> A7_HD void cube_lane_palette(const uint64_t *tab, int nlb, u
 	const uint64_t tx = tl[xy & 3u], ty = tl[4 + ((xy >> 2) & 3u)], tz = tl[8 + z];
 #pragma unroll
 	for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<2>(put_ramp_byte<1>(put_ramp_byte<0>(0u, tx, c), ty, c), tz, c);
+}
+
+// ---- byte-parallel helpers (native on the GPU) ---------------------------------------------------------------------
+A7_HD uint32_t vabsdiff4_u8(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+	return __vabsdiffu4(a, b);
+#else
+	uint32_t r = 0;
+	for (int k = 0; k < 4; k++) {
+		const int d = (int) ((a >> (8 * k)) & 255u) - (int) ((b >> (8 * k)) & 255u);
+		r |= (uint32_t) (d < 0 ? -d : d) << (8 * k);
+	}
+	return r;
+#endif
+}
+A7_HD uint32_t vmin4_u8(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+	return __vminu4(a, b);
+#else
+	uint32_t r = 0;
+	for (int k = 0; k < 4; k++) {
+		const uint32_t x = (a >> (8 * k)) & 255u, y = (b >> (8 * k)) & 255u;
+		r |= (x < y ? x : y) << (8 * k);
+	}
+	return r;
+#endif
+}
+A7_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t acc) {
+#if defined(__CUDA_ARCH__)
+	return __dp4a(a, b, acc);
+#else
+	for (int k = 0; k < 4; k++) acc += ((a >> (8 * k)) & 255u) * ((b >> (8 * k)) & 255u);
+	return acc;
+#endif
+}
+// ---- ramps from a difference table ---------------------------------------------------------------------------------
+// ramp entry c between expanded endpoints e1, e2 = floor((2 D e1 + D + 2 c (e2 - e1)) / (2 D)) = e1 + off(e2 - e1, c), and
+// every entry stays within 0 .. 255, so a whole ramp is a byte-parallel add (e2 >= e1) or subtract of a table word: no
+// carries between the bytes.  Table of C = 2^CLOG: words [a * H + h] for |e2 - e1| = a, H = C / 4 words per ramp; the
+// non-negative differences first, the negative ones kRampLutNeg<CLOG> words later.
+template <int CLOG> struct RampLutShape {
+	static constexpr int H = (1 << CLOG) / 4, kNeg = 256 * H, kWords = 512 * H;
+};
+template <int CLOG> A7_HD void ramp_lut_fill(uint32_t *lut, int first, int step) { // entries first, first + step, ... of the table
+	constexpr int C = 1 << CLOG, D = C - 1, H = C / 4;
+#pragma unroll 1
+	for (int id = first; id < 512 * H; id += step) {
+		const int neg = id >= 256 * H, a = (id - (neg ? 256 * H : 0)) / H, h = id % H;
+		uint32_t w = 0;
+#pragma unroll 1
+		for (int b = 0; b < 4; b++) {
+			const int c = 4 * h + b;
+			const int num = neg ? 2 * c * a - D : D + 2 * c * a;
+			const int off = neg ? (num <= 0 ? 0 : (num + 2 * D - 1) / (2 * D)) : num / (2 * D);
+			w |= (uint32_t) off << (8 * b);
+		}
+		lut[id] = w;
+	}
+}
+template <int CLOG> A7_HD uint32_t ramp_lut_word(const uint32_t *lut, int e1, int e2, int h) {
+	constexpr int H = (1 << CLOG) / 4;
+	const int dl = e2 - e1;
+	const uint32_t rep = (uint32_t) e1 * 0x01010101u;
+	return dl < 0 ? rep - lut[256 * H + (-dl) * H + h] : rep + lut[dl * H + h];
+}
+// table-lookup form of cube_tab_word
+template <int CLOG> A7_HD uint32_t cube_tab_word_lut(const uint32_t *lut, const uint32_t ep[6], int bcc, int id) {
+	constexpr int H = (1 << CLOG) / 4;
+	const int hf = id % H, rid = id / H;
+	const int x = rid & 3, lk = rid >> 2, l = lk / 3, k = lk - 3 * l;
+	const int odd = bcc ? (l >> 1) : l, flip = bcc ? (l & 1) : 0;
+	const int e1 = (int) ((ep[k] >> (16 * odd + 8 * (x & 1))) & 255u), e2 = (int) ((ep[3 + k] >> (16 * (odd ^ flip) + 8 * (x >> 1))) & 255u);
+	return ramp_lut_word<CLOG>(lut, e1, e2, hf);
 }
 
 // ep_shaker_d on packed 8-bit data (dimension 3). index_io in/out; returns the SSE (exact integer as real).
@@ -804,6 +877,135 @@ A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int
 							t += r * (cnt[c] * r - sum2[c]);
 						}
 						if (t < best) { best = t; b1 = p1; b2 = p2; }
+					}
+				}
+				ed[pp0][pp1][j] = best;
+				ep2[pp0][pp1][0][j] = b1;
+				ep2[pp0][pp1][1][j] = b2;
+			}
+	}
+	int64_t err_1 = INT64_MAX;
+	int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll 1
+	for (int pn = 0; pn < (1 << type); pn++) {
+		const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
+		int64_t e2 = 0;
+#pragma unroll 1
+		for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
+		if (e2 < err_1) {
+			err_1 = e2;
+#pragma unroll 1
+			for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
+		}
+	}
+	epo_out = pack_ep8(epo_1);
+	return (uint32_t) err_1;
+}
+
+// The same work item with the candidate ramps taken from the difference table and the error summed per TEXEL instead of
+// per cluster: the ramp of a candidate (p1, p2) is a 64-bit word, texel m's entry r[cidx[m]] is picked out of it by a
+// byte permute (4 texels per PRMT, selectors built once per item), and |r - d| / its square are 4-wide byte
+// instructions against the channel plane of the data -- 3 instructions per 4 texels and candidate.
+// sum_m (r[cidx[m]] - d[m])^2 is the same integer the cluster form computes, so the search is identical.
+A7_HD int endpoint_floor_int(real v, int bits, int use_par, int odd) { // ep_find_floor with the comparisons done on floor(v)
+	const int iv = (v >= 0) ? ((v >= 256.) ? 256 : (int) v) : -1;        // v >= x  <=>  floor(v) >= x for integer x; NaN -> -1
+	int i1 = 0, i2 = 1 << (bits - use_par);
+	odd = use_par ? odd : 0;
+	while (i2 - i1 > 1) {
+		const int j = (i1 + i2) / 2;
+		if (iv >= expand_bits(bits, (j << use_par) + odd)) i1 = j;
+		else i2 = j;
+	}
+	return (i1 << use_par) + odd;
+}
+A7_HD uint32_t perm_bytes(uint32_t lo, uint32_t hi, uint32_t sel) { // byte b of the result = byte (sel >> 4b & 7) of hi:lo
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(lo, hi, sel);
+#else
+	const uint64_t v = (uint64_t) lo | ((uint64_t) hi << 32);
+	uint32_t r = 0;
+	for (int b = 0; b < 4; b++) r |= (uint32_t) ((v >> (8 * ((sel >> (4 * b)) & 7u))) & 255u) << (8 * b);
+	return r;
+#endif
+}
+// plane[j * 4 + w] = channel j of texels 4w .. 4w+3 (pads 0), all four channels
+A7_HD void window_planes_u8(const uint32_t *d, int n, uint32_t plane[16]) {
+#pragma unroll 1
+	for (int j = 0; j < 4; j++)
+#pragma unroll 1
+		for (int w = 0; w < 4; w++) {
+			uint32_t v = 0;
+#pragma unroll 1
+			for (int b = 0; b < 4; b++)
+				if (4 * w + b < n) v |= ((d[4 * w + b] >> (8 * j)) & 255u) << (8 * b);
+			plane[j * 4 + w] = v;
+		}
+}
+template <int CLOG>
+A7_HDN uint32_t window_item_lut_u8(const uint32_t *lut, const uint32_t *d, const uint32_t *plane, int n, uint64_t collapsed, int q, int p, int size,
+																	 int bits_total, int dim, uint64_t &epo_out) {
+	constexpr int C = 1 << CLOG;
+	static_assert(C <= 8, "one 64-bit ramp");
+	const int type = bits_total % (2 * dim);
+	const int use_par = type != 0;
+	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
+	ClusterAcc<CLOG> cs;
+	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
+	real epa[2][4];
+	fit_endpoints_acc<CLOG>(cs, dim, epa);
+	const int nw = (n + 3) >> 2;
+	const uint32_t last = (n & 3) ? ((1u << (8 * (n & 3))) - 1u) : 0xffffffffu;
+	uint32_t sel[4];
+#pragma unroll
+	for (int w = 0; w < 4; w++) {
+		uint32_t sw = 0;
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const int k = 4 * w + b;
+			const uint32_t ck = k < n ? (uint32_t) ((collapsed >> (4 * k)) & 15u) * (uint32_t) q + (uint32_t) p : 0u;
+			sw |= ck << (4 * b);
+		}
+		sel[w] = sw;
+	}
+	int ed[2][2][4], ep2[2][2][2][4];
+	const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
+#pragma unroll 1
+	for (int j = 0; j < dim; j++) {
+		const uint32_t plw[4] = {plane[4 * j], plane[4 * j + 1], plane[4 * j + 2], plane[4 * j + 3]};
+		int fl[2][2];
+#pragma unroll
+		for (int i = 0; i < 2; i++)
+#pragma unroll
+			for (int par = 0; par < 2; par++) fl[i][par] = par < rr ? endpoint_floor_int(epa[i][j], mb, use_par, par) : 0;
+#pragma unroll 1
+		for (int pp0 = 0; pp0 < rr; pp0++)
+#pragma unroll 1
+			for (int pp1 = 0; pp1 < rr; pp1++) {
+				int lo[2], hi[2];
+#pragma unroll
+				for (int i = 0; i < 2; i++) {
+					const int pi = i ? pp1 : pp0;
+					const int f = pi ? fl[i][1] : fl[i][0];
+					lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
+					hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
+				}
+				int best = INT32_MAX, b1 = 0, b2 = 0;
+#pragma unroll 1
+				for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
+					const int e1 = expand_bits(mb, p1);
+#pragma unroll 1
+					for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
+						const int e2 = expand_bits(mb, p2);
+						const uint32_t r0 = ramp_lut_word<CLOG>(lut, e1, e2, 0), r1 = C > 4 ? ramp_lut_word<CLOG>(lut, e1, e2, C > 4 ? 1 : 0) : 0u;
+						uint32_t t = 0;
+#pragma unroll
+						for (int w = 0; w < 4; w++) { // (static indices: sel[] and the plane words stay in registers)
+							if (w >= nw) break;
+							uint32_t ad = vabsdiff4_u8(perm_bytes(r0, r1, sel[w]), plw[w]);
+							if (w == nw - 1) ad &= last;
+							t = dot4_u8(ad, ad, t);
+						}
+						if ((int) t < best) { best = (int) t; b1 = p1; b2 = p2; }
 					}
 				}
 				ed[pp0][pp1][j] = best;

@@ -5,7 +5,11 @@
 
 namespace b200ic {
 
-cudaError_t launch_bc45(const SrcImage &img, int channels, int first_channel, void *dst, cudaStream_t stream);
+cudaError_t launch_bc45(const SrcImage &img, int channels, int first_channel, void *dst, cudaStream_t stream, int dst_stride = 8);
+// BC2 / BC3: kBc3Colour = BC3 (alpha half by the BC4 kernel, colour half here), kBc2Both = BC2 (4-bit alpha + colour);
+// block API: kColourOnly / kAlphaOnly write one 8-byte half per block
+enum Bc23Part { kBc3Colour = 0, kBc2Both = 1, kColourOnly = 2, kAlphaOnly = 3 };
+cudaError_t launch_bc23(const SrcImage &img, const b200ic_opts &opts, int part, void *dst, cudaStream_t stream);
 cudaError_t launch_bc1(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
 cudaError_t launch_bc7rg(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
 cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);

@@ -34,13 +34,16 @@ extern "C" {
 
 typedef enum b200ic_codec {
 	B200IC_BC1 = 1,     /* AMD BC1, 8 B/block  (Image_CompressAMDBC1) */
-	B200IC_BC2 = 2,     /* reserved */
-	B200IC_BC3 = 3,     /* reserved */
+	B200IC_BC2 = 2,     /* AMD BC2, 16 B/block (Image_CompressAMDBC2: 4-bit explicit alpha + colour) */
+	B200IC_BC3 = 3,     /* AMD BC3, 16 B/block (Image_CompressAMDBC3: BC4 search on alpha + colour) */
 	B200IC_BC4 = 4,     /* AMD BC4, 8 B/block  (Image_CompressAMDBC4; encodes channel 1 like the reference) */
 	B200IC_BC5 = 5,     /* AMD BC5, 16 B/block (Image_CompressAMDBC5; channels 0,1) */
 	B200IC_BC6H = 6,    /* AMD BC6H, 16 B/block */
 	B200IC_BC7_AMD = 7, /* AMD BC7, 16 B/block (Image_CompressAMDBC7) */
-	B200IC_BC7_RG = 8   /* bc7enc16, 16 B/block (Image_CompressRichGel999BC7) */
+	B200IC_BC7_RG = 8,  /* bc7enc16, 16 B/block (Image_CompressRichGel999BC7) */
+	/* block API only: the two 8-byte halves of a BC2 / BC3 block on their own */
+	B200IC_BC23_COLOUR_HALF = 9, /* Image_CompressAMDRGBSingleModeBlock (F32X3 / F32X4 blocks) */
+	B200IC_BC2_ALPHA_HALF = 10   /* Image_CompressAMDExplictAlphaSingleModeBlock (F32X1 blocks) */
 } b200ic_codec;
 
 /* Source texel formats.  Values equal the TinyImageFormat tags of compat/tiny_imageformat. */
@@ -101,12 +104,27 @@ B200IC_API int b200ic_encode_device(int codec, const void *d_src, int format, ui
 																		const b200ic_opts *opts, void *d_dst, void *stream);
 
 /* Host-buffer encode: H2D of block-row chunks, kernels and D2H pipelined over internal streams.
- * Synchronous. `progress` (may be NULL) is called after each chunk with percent in [0,100); returning
+ * Pageable caller buffers are staged through pinned memory by the calling thread while the GPU works on the previous
+ * chunks; pinned / registered buffers are copied directly.  Synchronous.  `progress` (may be NULL) is called once per
+ * finished block-row, in order, with the reference's percentage (100 * y * blocksX / (blocksX * blocksY)); returning
  * non-zero cancels (the call then returns 1).  Mirrors Image_CompressProgressFunc semantics. */
 typedef int (*b200ic_progress_fn)(void *user, float percent);
 B200IC_API int b200ic_encode_host(int codec, const void *h_src, int format, uint32_t width, uint32_t height,
 																	uint64_t row_pitch_bytes, uint32_t slices, const b200ic_opts *opts, void *h_dst,
 																	b200ic_progress_fn progress, void *user);
+
+/* The same encode with the block-rows of the image sharded over `n_devices` GPUs of this process (devices
+ * 0 .. n_devices-1; <= 0 = every visible device), one host thread and one stream ring per device, every shard written
+ * straight into its range of h_dst -- no collective.  This is the loop of reference src/amd_bc7_compressor.cpp:48-77
+ * (and its siblings) split by block-row.  `progress` calls are serialised.  Synchronous. */
+B200IC_API int b200ic_encode_host_sharded(int codec, const void *h_src, int format, uint32_t width, uint32_t height,
+																					uint64_t row_pitch_bytes, uint32_t slices, const b200ic_opts *opts, void *h_dst,
+																					b200ic_progress_fn progress, void *user, int n_devices);
+
+/* How many GPUs the Image_Compress* entry points (include/gfx_imagecompress/imagecompress.h) shard a large image over:
+ * n >= 1 devices, 0 = every visible device (the default; the environment variable B200IC_DEVICES overrides the default). */
+B200IC_API void b200ic_set_devices(int n);
+B200IC_API int b200ic_get_devices(void);
 
 /* Batched block API on host buffers: `format` is one of B200IC_FMT_BLOCKS_*; nblocks pre-gathered blocks. */
 B200IC_API int b200ic_encode_blocks(int codec, const void *h_blocks, int format, uint64_t nblocks,
@@ -141,6 +159,13 @@ B200IC_API uint64_t b200ic_plan_shards(const uint32_t *widths, const uint32_t *h
  * spread over internal streams forked from / joined to `stream`, so small mip levels overlap.  Asynchronous. */
 B200IC_API int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint64_t n_images,
 																					const b200ic_shard *shards, uint64_t n_shards, const b200ic_opts *opts, void *stream);
+
+/* Per-kernel timing of the AMD BC7 pipeline (bench.py's roofline): while enabled, every kernel launch is bracketed by
+ * CUDA events on the launching stream.  b200ic_profile_read waits for the recorded events, adds their durations (ms)
+ * and counts into ms[mode * 4 + kind] / launches[mode * 4 + kind] (32 entries each; kind 0 quantise, 1 cube, 2 window,
+ * 3 thread-per-block kernel), clears the record and returns the number of launches read. */
+B200IC_API void b200ic_profile(int enable);
+B200IC_API int b200ic_profile_read(double *ms, uint64_t *launches);
 
 /* Number of kernel launches issued by this library since b200ic_init (for bench.py's gpu_launches). */
 B200IC_API uint64_t b200ic_launch_count(void);

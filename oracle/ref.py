@@ -140,6 +140,8 @@ class Decoders:
         L.bcdec_bc1.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.bcdec_bc7.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.bcdec_bc45.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        L.bcdec_bc23.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+        L.bcdec_bc6h.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
 
     def bc1(self, blocks: np.ndarray, w: int, h: int) -> np.ndarray:
         b = np.ascontiguousarray(blocks, np.uint8)
@@ -159,3 +161,18 @@ class Decoders:
         out = np.zeros((h, w, nch), np.uint8)
         self.lib.bcdec_bc45(b.ctypes.data, w, h, nch, out.ctypes.data)
         return out
+
+    def bc23(self, blocks: np.ndarray, w: int, h: int, explicit_alpha: bool) -> np.ndarray:
+        """BC2 (explicit_alpha) / BC3 blocks -> (h, w, 4) uint8."""
+        b = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((h, w, 4), np.uint8)
+        self.lib.bcdec_bc23(b.ctypes.data, w, h, int(explicit_alpha), out.ctypes.data)
+        return out
+
+    def bc6h(self, blocks: np.ndarray, w: int, h: int, is_signed: bool = False, with_modes: bool = False):
+        """BC6H blocks -> (h, w, 3) float16."""
+        b = np.ascontiguousarray(blocks, np.uint8)
+        out = np.zeros((h, w, 3), np.uint16)
+        hist = np.zeros(15, np.uint32)
+        self.lib.bcdec_bc6h(b.ctypes.data, w, h, int(is_signed), out.ctypes.data, hist.ctypes.data)
+        return (out.view(np.float16), hist) if with_modes else out.view(np.float16)

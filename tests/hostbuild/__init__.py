@@ -40,6 +40,8 @@ def load():
         L.hb_bc1_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
     if hasattr(L, "hb_bc7amd_blocks"):
         L.hb_bc7amd_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    if hasattr(L, "hb_bc23_colour_blocks"):
+        L.hb_bc23_colour_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     if hasattr(L, "hb_cube_lane_check"):
         L.hb_cube_lane_check.argtypes = [C.c_uint64, C.c_int]
     return L
@@ -72,4 +74,11 @@ def bc6h_blocks(L, blocks_f32: np.ndarray, is_signed: bool = False) -> np.ndarra
     b = np.ascontiguousarray(blocks_f32, np.float32).reshape(-1, 64)
     out = np.zeros((len(b), 16), np.uint8)
     L.hb_bc6h_blocks(b.ctypes.data, len(b), int(is_signed), out.ctypes.data)
+    return out
+
+
+def bc23_colour_blocks(L, blocks_f32: np.ndarray, steps: int = 1) -> np.ndarray:
+    b = np.ascontiguousarray(blocks_f32, np.float32).reshape(-1, 64)
+    out = np.zeros((len(b), 8), np.uint8)
+    L.hb_bc23_colour_blocks(b.ctypes.data, len(b), steps, out.ctypes.data)
     return out

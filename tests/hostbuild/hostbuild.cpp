@@ -42,6 +42,18 @@ void hb_bc1_blocks(const float *in, uint64_t nblocks, float alpha_threshold, int
 	}
 }
 #endif
+#ifdef HB_BC1
+// colour half of BC2 / BC3 as this repo defines it: the BC1 4-point fit without punch-through; in: nblocks x 64 floats
+void hb_bc23_colour_blocks(const float *in, uint64_t nblocks, int steps, uint8_t *out) {
+	for (uint64_t b = 0; b < nblocks; b++) {
+		uint8_t ep[3][2], idx[16];
+		uint32_t w[2];
+		b200ic::bc1::compress(in + b * 64, 4, false, 0.0f, steps, ep, idx);
+		b200ic::bc1::pack_fit(1, ep, idx, w);
+		memcpy(out + b * 8, w, 8);
+	}
+}
+#endif
 #ifdef HB_BC7AMD
 static uint32_t *hb_sp_table() {
 	static std::vector<uint32_t> sp;
@@ -70,9 +82,9 @@ void hb_bc7amd_blocks(const float *in, uint64_t nblocks, uint32_t mode_mask, uin
 }
 #endif
 #ifdef HB_BC7AMD
+}
 // The lane = corner form of the cube walk (bc7amd_int.cuh, what the CUDA cube kernel runs) emulated lane by lane
 // against the serial cube_search_u8 on random items. Returns the number of items whose (key, indices) differ.
-}
 template <int CLOG> static int hb_cube_lane_trial(uint64_t &rng, int bits, int type) {
 	using namespace b200ic::amd7;
 	auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t) (rng >> 33); };
@@ -109,8 +121,12 @@ template <int CLOG> static int hb_cube_lane_trial(uint64_t &rng, int bits, int t
 	const int nl = (use_par + 1) * (bcc + 1), nlb = nl == 4 ? 2 : (nl == 2 ? 1 : 0);
 	uint64_t tab[4 * 12] = {};
 	constexpr int H = C / 4;
+	static std::vector<uint32_t> lut; // the difference-table ramps the kernel uses must equal the computed ones
+	if (lut.empty()) { lut.resize(RampLutShape<CLOG>::kWords); ramp_lut_fill<CLOG>(lut.data(), 0, 1); }
+	int bad_tab = 0;
 	for (int id = 0; id < nl * 12 * H; id++) {
-		const uint32_t w = cube_tab_word<CLOG>(ep, bcc, id);
+		const uint32_t w = cube_tab_word_lut<CLOG>(lut.data(), ep, bcc, id);
+		if (w != cube_tab_word<CLOG>(ep, bcc, id)) bad_tab = 1;
 		tab[id / H] |= (uint64_t) w << (32 * (id % H));
 	}
 	uint32_t best = 0xffffffffu, best_xy = 0;
@@ -123,7 +139,60 @@ template <int CLOG> static int hb_cube_lane_trial(uint64_t &rng, int bits, int t
 	uint32_t pal[C];
 	cube_lane_palette<CLOG>(tab, nlb, best_lane, best_xy, pal);
 	const uint64_t got_idx = palette_indices_u8<CLOG>(d, n, pal);
-	return (best != want_key || got_idx != want_idx) ? 1 : 0;
+	return (bad_tab || best != want_key || got_idx != want_idx) ? 1 : 0;
+}
+// window_item_lut_u8 (table ramps, per-texel sums) against window_item_u8 (cluster sums) on random items
+template <int CLOG> static int hb_window_trial(uint64_t &rng, int size, int bits_total, int dim) {
+	using namespace b200ic::amd7;
+	auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t) (rng >> 33); };
+	constexpr int C = 1 << CLOG;
+	static std::vector<uint32_t> lut;
+	if (lut.empty()) { lut.resize(RampLutShape<CLOG>::kWords); ramp_lut_fill<CLOG>(lut.data(), 0, 1); }
+	const int n = 2 + (int) (next() % 15);
+	uint32_t d[16] = {};
+	const uint32_t base = next(), spread = 1u << (next() % 9);
+	for (int i = 0; i < n; i++) {
+		uint32_t v = 0;
+		for (int j = 0; j < dim; j++) v |= ((((base >> (8 * j)) & 255u) + next() % spread) & 255u) << (8 * j);
+		d[i] = v;
+	}
+	int idx[16];
+	for (int i = 0; i < n; i++) idx[i] = (int) (next() % C);
+	idx[0] = 0;
+	idx[n - 1] = 1 + (int) (next() % (C - 1));
+	const int Mi = collapse_indices(idx, n);
+	if (Mi == 0) return 0;
+	uint64_t cur = 0;
+	for (int i = 0; i < n; i++) cur |= (uint64_t) idx[i] << (4 * i);
+	int q, p;
+	qp_decode((int) (next() % qp_count(Mi, C - 1)), Mi, C - 1, q, p);
+	uint32_t plane[16];
+	window_planes_u8(d, n, plane);
+	uint64_t ea, eb;
+	const uint32_t a = window_item_u8<CLOG>(d, n, cur, q, p, size, bits_total, dim, ea);
+	const uint32_t b = window_item_lut_u8<CLOG>(lut.data(), d, plane, n, cur, q, p, size, bits_total, dim, eb);
+	return (a != b || ea != eb) ? 1 : 0;
+}
+extern "C" int hb_window_check(uint64_t seed, int trials) {
+	using namespace b200ic::amd7;
+	uint64_t rng = seed * 2 + 1;
+	int bad = 0;
+	for (int t = 0; t < trials; t++) {
+		for (int mode = 0; mode < 8; mode++) {
+			if (mode == 6) continue;
+			const ModeInfo mi = mode_info(mode);
+			if (mi.alpha == 2) {
+				bad += hb_window_trial<2>(rng, 6, 6 * (mi.vector_bits / 3), 3);
+				if (mode == 4) bad += hb_window_trial<3>(rng, 6, 6 * mi.scalar_bits, 3);
+				else bad += hb_window_trial<2>(rng, 6, 6 * mi.scalar_bits, 3);
+			} else {
+				const ShakeParams sp = single_index_shake_params(mode);
+				if (sp.clusters == 8) bad += hb_window_trial<3>(rng, sp.shake_size, sp.bits[3], sp.dim);
+				else bad += hb_window_trial<2>(rng, sp.shake_size, sp.bits[3], sp.dim);
+			}
+		}
+	}
+	return bad;
 }
 extern "C" {
 int hb_cube_lane_check(uint64_t seed, int trials) {

@@ -26,4 +26,6 @@ for kind in ("opaque", "ramp"):
         ms = e0.elapsed_time(e1) / 2
         if mask != 0xFF:
             tot += ms
-        print(f"{kind:7s} mask {mask:#04x}: {ms:8.2f} ms  {n * n / 16 / ms / 1e3:8.2f} Mblocks/s" + (f"   (sum of single modes {tot:.2f} ms)" if mask == 0xFF else ""), flush=True)
+        import subprocess
+        clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+        print(f"[{clk}] {kind:7s} mask {mask:#04x}: {ms:8.2f} ms  {n * n / 16 / ms / 1e3:8.2f} Mblocks/s" + (f"   (sum of single modes {tot:.2f} ms)" if mask == 0xFF else ""), flush=True)

@@ -12,8 +12,8 @@ from gfx_imagecompress_b200 import synth
 L = g.load_library(); g.init(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 dev = torch.device("cuda", 0)
-names = ["quantise", "rank+setup", "cube", "window", "window2", "pick+pack", "cube items", "cube rounds", "win items", "win rounds", "cube passes"]
-for kind, modes in (("opaque", (0, 1, 2, 3)), ("ramp", (7,))):
+names = ["quantise", "rank", "cube", "window", "window2", "pick+pack", "cube items", "cube batches", "win items", "win rounds", "cube passes"]
+for kind, modes in (("opaque", (0, 1, 2, 3, 4, 5)), ("ramp", (4, 5, 7))):
     px = torch.from_numpy(synth.rgba8_gradnoise(n, n, 3, kind)).to(dev)
     out = torch.empty((n * n // 16, 16), dtype=torch.uint8, device=dev)
     nb = n * n // 16

@@ -20,12 +20,21 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "n
 def read(path):
     """`path` is the --csv --log-file of `ncu --metrics ...` (one row per launch and metric)."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0] != "ID" and not r[0].startswith("==")]
-    out = dict(launches=0, dram_bytes=0.0, warp_inst=0.0, thread_inst=0.0, time_s=0.0, kernels=[])
+    out = dict(launches=0, dram_bytes=0.0, warp_inst=0.0, thread_inst=0.0, time_s=0.0, kernels=[], per_launch={})
     ids = set()
     for r in rows:
         kid, kernel, metric, unit, value = r[0], r[4], r[-3], r[-2], float(r[-1].replace(",", ""))
         value *= UNIT.get(unit, 1.0)
         ids.add(kid)
+        pl = out["per_launch"].setdefault(int(kid), dict(kernel=kernel.split("(")[0].split("::")[-1], dram_bytes=0.0, warp_inst=0.0, thread_inst=0.0, time_s=0.0))
+        if metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            pl["dram_bytes"] += value
+        elif metric == "smsp__inst_executed.sum":
+            pl["warp_inst"] += value
+        elif metric == "smsp__thread_inst_executed.sum":
+            pl["thread_inst"] += value
+        elif metric == "gpu__time_duration.sum":
+            pl["time_s"] += value
         if kernel not in out["kernels"]:
             out["kernels"].append(kernel)
         if metric in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -37,6 +46,7 @@ def read(path):
         elif metric == "gpu__time_duration.sum":
             out["time_s"] += value
     out["launches"] = len(ids)
+    out["per_launch"] = [out["per_launch"][k] for k in sorted(out["per_launch"])]
     return out
 
 
@@ -51,6 +61,8 @@ def main(args):
         db[codec] = {"report": os.path.basename(rep), "blocks": b, "launches_per_encode": c["launches"], "kernels": c["kernels"],
                      "dram_bytes_per_block": c["dram_bytes"] / b, "warp_inst_per_block": c["warp_inst"] / b,
                      "thread_inst_per_block": c["thread_inst"] / b, "kernel_time_s_under_ncu": c["time_s"]}
+        if c["launches"] > 1:  # AMD BC7: one record per launch of the encode, in launch order (bench.py maps them to (mode, phase))
+            db[codec]["per_launch"] = c["per_launch"]
         print(codec, db[codec])
     json.dump(db, open(path, "w"), indent=1, sort_keys=True)
 
