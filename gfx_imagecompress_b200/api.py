@@ -89,6 +89,8 @@ def load_library(path: str | None = None):
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.b200ic_set_devices.argtypes = [C.c_int]
     L.b200ic_device_count.restype = C.c_int
+    L.b200ic_box_mip_rgba8_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.b200ic_write_dds.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.b200ic_encode_blocks.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     L.b200ic_plan_shards.restype = C.c_uint64
     L.b200ic_plan_shards.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -215,6 +217,30 @@ def encode_blocks(codec: int, blocks: np.ndarray, fmt: int, opts: Opts | None = 
     _check(L.b200ic_encode_blocks(codec, blocks.ctypes.data, fmt, n, C.byref(opts) if opts is not None else None,
                                   out.ctypes.data), "b200ic_encode_blocks")
     return out
+
+
+def box_mip_chain(top, stream=None):
+    """Full mip chain of an (H, W, 4) uint8 CUDA tensor down to 1x1 with b200ic_box_mip_rgba8_device."""
+    import torch
+    L = library()
+    assert top.is_cuda and top.is_contiguous() and top.dtype == torch.uint8 and top.shape[2] == 4
+    chain = [top]
+    st = stream if stream is not None else torch.cuda.current_stream(top.device).cuda_stream
+    with torch.cuda.device(top.device):
+        while chain[-1].shape[0] > 1 or chain[-1].shape[1] > 1:
+            s = chain[-1]
+            h, w = int(s.shape[0]), int(s.shape[1])
+            d = torch.empty((max(1, h // 2), max(1, w // 2), 4), dtype=torch.uint8, device=top.device)
+            _check(L.b200ic_box_mip_rgba8_device(s.data_ptr(), w, h, 0, d.data_ptr(), 0, st), "b200ic_box_mip_rgba8_device")
+            chain.append(d)
+    return chain
+
+
+def write_dds(path: str, codec: int, width: int, height: int, levels, srgb: bool = False, is_signed: bool = False) -> None:
+    """b200ic_write_dds: `levels` = list of (nblocks, blockBytes) uint8 arrays, top level first."""
+    arrs = [np.ascontiguousarray(a, np.uint8) for a in levels]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    _check(library().b200ic_write_dds(path.encode(), codec, int(srgb), int(is_signed), width, height, len(arrs), ptrs), "b200ic_write_dds")
 
 
 class ImageDesc(C.Structure):

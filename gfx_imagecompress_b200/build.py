@@ -25,6 +25,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 # (source, extra flags)
 UNITS = [
     ("api.cu", []),
+    ("container.cu", []),
     ("bc45.cu", ["--fmad=false"]),
     ("bc1.cu", ["--fmad=false"]),
     ("bc7rg.cu", ["--fmad=false"]),

@@ -177,6 +177,13 @@ static int ensure_device() {
 			cudaDeviceProp prop;
 			B200IC_CUDA(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
 			if (prop.major < 10) return fail("device is not sm_100-class; kernels are built for sm_100a only");
+			{ // the per-encode scratch of the AMD BC7 pipeline comes from the stream-ordered pool: keep it cached between encodes
+				cudaMemPool_t pool;
+				if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+					uint64_t keep = 2ull << 30;
+					cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+				}
+			}
 			B200IC_CUDA(init_bc7rg_tables(), "bc7enc16 table upload");
 			B200IC_CUDA(init_bc7amd_tables(), "BC7 table upload");
 			B200IC_CUDA(init_bc6h_tables(), "BC6H table upload");
@@ -564,6 +571,28 @@ int b200ic_encode_blocks(int codec, const void *h_blocks, int format, uint64_t n
 	if (b200ic_encode_device(codec, cx.d_in[0], format, (uint32_t) nblocks, 1, 0, 0, 1, opts, cx.d_out[0], st)) return -1;
 	B200IC_CUDA(cudaMemcpyAsync(h_dst, cx.d_out[0], (size_t) nblocks * bb, cudaMemcpyDeviceToHost, st), "D2H copy");
 	B200IC_CUDA(cudaStreamSynchronize(st), "encode blocks");
+	return 0;
+}
+
+int b200ic_box_mip_rgba8_device(const void *d_src, uint32_t width, uint32_t height, uint64_t src_pitch_bytes, void *d_dst, uint64_t dst_pitch_bytes,
+																void *stream) {
+	t_error.clear();
+	if (!d_src || !d_dst) return fail("null buffer");
+	if (width == 0 || height == 0) return fail("empty image");
+	if (((uintptr_t) d_src | (uintptr_t) d_dst | src_pitch_bytes | dst_pitch_bytes) & 3u) return fail("RGBA8 levels must be 4-byte aligned");
+	if (ensure_device()) return -1;
+	B200IC_CUDA(launch_box_mip_rgba8(d_src, width, height, src_pitch_bytes, d_dst, dst_pitch_bytes, static_cast<cudaStream_t>(stream)), "mip kernel launch");
+	g_launches.fetch_add(1, std::memory_order_relaxed);
+	return 0;
+}
+
+int b200ic_write_dds(const char *path, int codec, int srgb, int is_signed, uint32_t width, uint32_t height, uint32_t levels,
+										 const void *const *level_blocks) {
+	t_error.clear();
+	const int rc = write_dds(path, codec, srgb, is_signed, width, height, levels, level_blocks);
+	if (rc == -1) return fail("b200ic_write_dds: bad arguments");
+	if (rc == -2) return fail("b200ic_write_dds: cannot open the file");
+	if (rc != 0) return fail("b200ic_write_dds: short write");
 	return 0;
 }
 

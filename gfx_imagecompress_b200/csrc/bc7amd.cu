@@ -35,7 +35,6 @@ using namespace amd7;
 
 constexpr int kWarps = 4;
 constexpr int kMaxTasks = 24;   // single-index: 8 attempts x 3 subsets; dual-index: 8 combos x 2
-constexpr int kItemBatch = 160; // window phase: work items evaluated between two per-task reductions
 constexpr uint32_t kChunkBlocks = 1u << 19; // blocks per pass over the phase kernels (bounds the scratch: 584 B per block)
 
 uint32_t *g_sp_table_host[16] = {};
@@ -370,36 +369,14 @@ __global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdPara
 	}
 	const ModeInfo mi = mode_info(mode);
 	AMD_T0();
-	if (mi.alpha == 2) { // dual-index modes: one 16-texel problem per (rotation, index selection, vector | scalar)
-		const DualShape ds = dual_shape(mi);
-		if ((int) lane < ds.ntasks) {
-			const int combo = (int) lane >> 1, which = (int) lane & 1;
-			const int rot = combo / ds.nsel, isel = combo - rot * ds.nsel;
-			const uint32_t c0 = (uint32_t) rotation_channel(rot, 0), c1 = (uint32_t) rotation_channel(rot, 1),
-										 c2 = (uint32_t) rotation_channel(rot, 2), c3 = (uint32_t) rotation_channel(rot, 3);
-			QuantIO io;
-			io.px = &ws.B.pxc[0][0];
-			io.texels = 0xFEDCBA9876543210ull;
-			io.chan = which == 0 ? (c1 | (c2 << 2) | (c3 << 4)) : (c0 | (c0 << 2) | (c0 << 4));
-			io.proj = &ws.qs[0][0][lane];
-			io.dev = &ws.qs[1][0][lane];
-			io.stride = 32;
-			uint64_t qpacked = 0;
-			quantise_subset(io, 16, 1 << dual_index_bits(mi, isel, which), 3, qpacked);
-			p.s.q_idx[(size_t) block * kMaxTasks + lane] = qpacked;
-		}
-		if (lane == 0) p.s.q_top[(size_t) block * 8] = 0;
-		AMD_T(0);
-		return;
-	}
 	const ShakeParams sp = single_index_shake_params(mode);
 	const int nparts = 1 << mi.partition_bits, subsets = mi.subsets;
 	const uint8_t *qorder = quantise_order(subsets, nparts);
-	QuantIO io;
-	io.px = &ws.B.pxc[0][0];
+	QuantIOShared io;
+	io.px = (uint32_t) __cvta_generic_to_shared(&ws.B.pxc[0][0]);
 	io.chan = 0xE4u;
-	io.proj = &ws.qs[0][0][lane];
-	io.dev = &ws.qs[1][0][lane];
+	io.proj = (uint32_t) __cvta_generic_to_shared(&ws.qs[0][0][lane]);
+	io.dev = (uint32_t) __cvta_generic_to_shared(&ws.qs[1][0][lane]);
 	io.stride = 32;
 	for (int tt = (int) lane; tt < nparts * subsets; tt += 32) {
 		const int t = qorder[tt];
@@ -436,6 +413,83 @@ __global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdPara
 	}
 	if (lane < 8) p.s.q_top[(size_t) block * 8 + lane] = (uint8_t) ws.top[lane];
 	AMD_T(1);
+}
+
+// Dual-index modes 4 / 5: 16 / 8 quantiser problems per block, all on the 16 texels of the block -- a warp takes 2 / 4
+// blocks so that its lanes are full: lane = (block of the warp, rotation, index selection, vector | scalar).
+struct DualQuantScratch {
+	float in[4][64];
+	BlockInput B[4];
+	real qs[2][16][32];
+};
+__global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_dual_kernel(const AmdParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	DualQuantScratch *scratch = reinterpret_cast<DualQuantScratch *>(smem_raw);
+	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+	const ModeInfo mi = mode_info(p.mode);
+	const DualShape ds = dual_shape(mi);
+	const int bpw = 32 / ds.ntasks; // blocks per warp
+	const uint32_t block0 = (blockIdx.x * kWarps + warp) * (uint32_t) bpw;
+	if (block0 >= p.n_blocks) return; // whole warp
+	DualQuantScratch &ws = scratch[warp];
+	AMD_T0();
+	for (int pass = 0; pass < (bpw + 1) / 2; pass++) { // block set-up, two blocks (16 lanes each) at a time
+		const int sub = pass * 2 + ((int) lane >> 4), tx = (int) lane & 15;
+		const bool have = sub < bpw && block0 + sub < p.n_blocks;
+		bool na = false, zo = false;
+		real v[4] = {0, 0, 0, 0};
+		if (have) {
+			const BlockCoord bc = block_coord(p, block0 + sub);
+			const float4 t = fetch_rgba(p.img, bc.gblock, bc.bx, bc.by, bc.slice, tx);
+			const float in4[4] = {t.x, t.y, t.z, t.w};
+			if (t.w < 1.0) na = true;
+			else if (((double) t.w >= 0.99999) || ((double) t.w < 0.00001)) zo = true;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				v[j] = (real) (in4[j] * 255.0f);
+				ws.B[sub].px[tx][j] = v[j];
+				ws.B[sub].pxc[j][tx] = v[j];
+			}
+		}
+		const unsigned half = 0xffffu << (lane & 16u);
+		const bool needs_alpha = (__ballot_sync(FULL, na) & half) != 0, zero_one = (__ballot_sync(FULL, zo) & half) != 0;
+		real range = 0;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			real mn = v[j], mx = v[j] > 0 ? v[j] : 0; // the reference's running maximum starts at 0
+			for (int d = 8; d > 0; d >>= 1) { // (xor distances below 16 stay inside the block's 16 lanes)
+				const real mn2 = __shfl_xor_sync(FULL, mn, d), mx2 = __shfl_xor_sync(FULL, mx, d);
+				mn = mn2 < mn ? mn2 : mn;
+				mx = mx2 > mx ? mx2 : mx;
+			}
+			const real r = mx - mn;
+			range = j == 0 ? r : (range > r ? range : r);
+		}
+		if (have && tx == 0) {
+			const uint32_t mm = filter_modes(p.mode_mask, needs_alpha, zero_one, range < 1e-10);
+			ws.B[sub].mode_mask = mm;
+			p.s.q_top[(size_t) (block0 + sub) * 8] = (mm & p.launch_modes & (1u << p.mode)) ? 0 : 0xffu;
+		}
+	}
+	__syncwarp();
+	const int sub = (int) lane / ds.ntasks, tk = (int) lane - sub * ds.ntasks;
+	if (sub < bpw && block0 + sub < p.n_blocks && (ws.B[sub].mode_mask & p.launch_modes & (1u << p.mode))) {
+		const int combo = tk >> 1, which = tk & 1;
+		const int rot = combo / ds.nsel, isel = combo - rot * ds.nsel;
+		const uint32_t c0 = (uint32_t) rotation_channel(rot, 0), c1 = (uint32_t) rotation_channel(rot, 1),
+									 c2 = (uint32_t) rotation_channel(rot, 2), c3 = (uint32_t) rotation_channel(rot, 3);
+		QuantIOShared io;
+		io.px = (uint32_t) __cvta_generic_to_shared(&ws.B[sub].pxc[0][0]);
+		io.texels = 0xFEDCBA9876543210ull;
+		io.chan = which == 0 ? (c1 | (c2 << 2) | (c3 << 4)) : (c0 | (c0 << 2) | (c0 << 4));
+		io.proj = (uint32_t) __cvta_generic_to_shared(&ws.qs[0][0][lane]);
+		io.dev = (uint32_t) __cvta_generic_to_shared(&ws.qs[1][0][lane]);
+		io.stride = 32;
+		uint64_t qpacked = 0;
+		quantise_subset(io, 16, 1 << dual_index_bits(mi, isel, which), 3, qpacked);
+		p.s.q_idx[(size_t) (block0 + sub) * kMaxTasks + tk] = qpacked;
+	}
+	AMD_T(0);
 }
 
 // =====================================================================================================================
@@ -649,12 +703,17 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 // =====================================================================================================================
 // window kernel (ep_shaker_2_d, best attempt, packing)
 // =====================================================================================================================
-struct WindowScratch {
+constexpr int kWinBatch = 32; // work items per batch of the window phase
+struct __align__(16) WindowScratch {
 	Task task[kMaxTasks];
-	uint64_t item_key[kItemBatch];
-	uint64_t item_idx[kItemBatch];
+	uint64_t item_key[kWinBatch];
+	uint64_t item_idx[kWinBatch];
+	uint64_t wres[kWinBatch][16]; // window_sub_search_u8 results of the batch: [item][channel * 4 + pp0 * 2 + pp1]
+	real wepa[kWinBatch][8];      // window_item_fit_u8: least-squares endpoints [endpoint * 4 + channel]
+	uint32_t wsel[kWinBatch][4];  //                     byte-permute selectors
 	ShakeOut so[kMaxTasks];
 	uint32_t px[16];
+	uint8_t item_ti[kWinBatch], item_qp[kWinBatch];
 	uint8_t order[kMaxTasks];
 	uint8_t top[8];
 };
@@ -711,25 +770,54 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, co
 		if (total == 0) break;
 		AMD_COUNT(8, total);
 		AMD_COUNT(9, (total + 31) / 32);
-		for (int b0 = 0; b0 < total; b0 += kItemBatch) {
-			const int b1 = min(total, b0 + kItemBatch);
-			for (int it = b0 + (int) lane; it < b1; it += 32) {
-				const Task &t = ws.task[item_owner(ws, ntasks, it)];
+		// every task of a launch has the same dimension and parity type (the endpoint bits differ between the vector and
+		// scalar tasks of the dual-index modes): dim x (1 | 2 | 4) independent searches per item
+		const int dim = ws.task[0].dim, type = ws.task[0].w_bits_total % (2 * dim), use_par = type != 0;
+		const int ncombo = type == BCC ? 4 : (type == SAME_PAR ? 2 : 1), per = dim * ncombo;
+		const int nbatch = (total + kWinBatch - 1) / kWinBatch, batch = (total + nbatch - 1) / nbatch; // (even batches)
+		for (int b0 = 0; b0 < total; b0 += batch) {
+			const int cnt = min(batch, total - b0);
+			if ((int) lane < cnt) { // fit: one item per lane
+				const int it = b0 + (int) lane, ti = item_owner(ws, ntasks, it);
+				const Task &t = ws.task[ti];
 				const int qp = it - t.item_base;
 				int q, p;
 				qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
+				real epa[8];
+				uint32_t sel[4];
+				if (t.clog == 2) window_item_fit_u8<2>(t.d, t.n, t.cur, q, p, dim, epa, sel);
+				else window_item_fit_u8<3>(t.d, t.n, t.cur, q, p, dim, epa, sel);
+#pragma unroll
+				for (int k = 0; k < 8; k++) ws.wepa[lane][k] = epa[k];
+#pragma unroll
+				for (int k = 0; k < 4; k++) ws.wsel[lane][k] = sel[k];
+				ws.item_ti[lane] = (uint8_t) ti;
+				ws.item_qp[lane] = (uint8_t) qp;
+			}
+			__syncwarp();
+			for (int sub = (int) lane; sub < cnt * per; sub += 32) { // search: one (item, channel, parity combination) per lane
+				const int item = sub / per, rest = sub - item * per, j = rest / ncombo, combo = rest - j * ncombo;
+				const int pp0 = type == SAME_PAR ? combo : (combo >> 1), pp1 = type == SAME_PAR ? combo : (combo & 1);
+				const Task &t = ws.task[ws.item_ti[item]];
+				const int mb = (t.w_bits_total + 2 * dim - 1) / (2 * dim);
+				const uint4 sv = *reinterpret_cast<const uint4 *>(ws.wsel[item]);
+				const uint4 pv = *reinterpret_cast<const uint4 *>(t.plane + 4 * j);
+				const uint32_t sel[4] = {sv.x, sv.y, sv.z, sv.w}, plw[4] = {pv.x, pv.y, pv.z, pv.w};
+				const real ep0 = ws.wepa[item][j], ep1 = ws.wepa[item][4 + j];
+				ws.wres[item][j * 4 + pp0 * 2 + pp1] = t.clog == 2 ? window_sub_search_u8<2>(lut2, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1)
+																													 : window_sub_search_u8<3>(lut3, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1);
+			}
+			__syncwarp();
+			if ((int) lane < cnt) { // combine
 				uint64_t epo;
-				uint32_t err;
-				if (t.clog == 2) err = window_item_lut_u8<2>(lut2, t.d, t.plane, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
-				else if (t.clog == 3) err = window_item_lut_u8<3>(lut3, t.d, t.plane, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
-				else err = window_item_u8<4>(t.d, t.n, t.cur, q, p, t.w_size, t.w_bits_total, t.dim, epo);
-				ws.item_key[it - b0] = ((uint64_t) err << 8) | (uint64_t) (255 - qp); // `<=`: the LAST minimum wins
-				ws.item_idx[it - b0] = epo;
+				const uint32_t err = window_item_combine(ws.wres[lane], type, dim, epo);
+				ws.item_key[lane] = ((uint64_t) err << 8) | (uint64_t) (255 - ws.item_qp[lane]); // `<=`: the LAST minimum wins
+				ws.item_idx[lane] = epo;
 			}
 			__syncwarp();
 			if ((int) lane < ntasks && !ws.task[lane].done) {
 				Task &t = ws.task[lane];
-				const int lo = max(b0, (int) t.item_base), hi = min(b1, (int) t.item_base + (int) t.item_count);
+				const int lo = max(b0, (int) t.item_base), hi = min(b0 + cnt, (int) t.item_base + (int) t.item_count);
 				for (int it = lo; it < hi; it++)
 					if (ws.item_key[it - b0] < t.pass_key) {
 						t.pass_key = ws.item_key[it - b0];
@@ -747,8 +835,7 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, co
 			uint64_t idg;
 			uint32_t err_r;
 			if (t.clog == 2) err_r = recluster_u8<2>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
-			else if (t.clog == 3) err_r = recluster_u8<3>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
-			else err_r = recluster_u8<4>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
+			else err_r = recluster_u8<3>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
 			int change = 0;
 			for (int k = 0; k < t.n; k++) change = change || ((int) ((t.cur >> (4 * k)) & 15u) * q0 + p0 != (int) ((idg >> (4 * k)) & 15u));
 			const int better = (real) err_r < t.w_err_o;
@@ -900,19 +987,20 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 }
 
 
-constexpr int kWindowCtasPerSm = 4;
-__global__ void __launch_bounds__(kWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
+// 8 warps per CTA: 2 CTAs (16 warps) fit the 227 KB of shared memory next to one copy of the ramp tables each
+constexpr int kWindowWarps = 8, kWindowCtasPerSm = 2;
+__global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WindowScratch *scratch = reinterpret_cast<WindowScratch *>(smem_raw);
 	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
-	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWarps * 32);
-	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWarps * 32);
+	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWindowWarps * 32);
+	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWindowWarps * 32);
 	__syncthreads();
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 	WindowScratch &ws = scratch[warp];
 	const Tables T{p.sp};
 #pragma unroll 1
-	for (uint32_t block = blockIdx.x * kWarps + warp; block < p.n_blocks; block += gridDim.x * kWarps)
+	for (uint32_t block = blockIdx.x * kWindowWarps + warp; block < p.n_blocks; block += gridDim.x * kWindowWarps)
 		window_block(p, ws, T, lut2, lut3, block, lane);
 }
 
@@ -1259,7 +1347,9 @@ cudaError_t init_bc7amd_tables() {
 	}
 	e = cudaFuncSetAttribute(amd_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(QuantScratch)));
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(WindowScratch)));
+	e = cudaFuncSetAttribute(amd_quant_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(DualQuantScratch)));
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(amd_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch)));
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(bc7amd_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(FloatScratch)));
 	if (e != cudaSuccess) return e;
@@ -1309,7 +1399,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 		p.block0 = b0;
 		p.n_blocks = (uint32_t) (total_blocks - b0 < chunk ? total_blocks - b0 : chunk);
 		const unsigned warp_grid = (p.n_blocks + kWarps - 1) / kWarps;
-		const unsigned window_grid = warp_grid < (unsigned) (sms * kWindowCtasPerSm * kWaves) ? warp_grid : (unsigned) (sms * kWindowCtasPerSm * kWaves);
+		const unsigned window_ctas = (p.n_blocks + kWindowWarps - 1) / kWindowWarps;
+		const unsigned window_grid = window_ctas < (unsigned) (sms * kWindowCtasPerSm * kWaves) ? window_ctas : (unsigned) (sms * kWindowCtasPerSm * kWaves);
 		const unsigned cube_grid = warp_grid < (unsigned) (sms * kCubeCtasPerSm * kWaves) ? warp_grid : (unsigned) (sms * kCubeCtasPerSm * kWaves);
 		int passes = 0;
 		for (int vi = 0; vi < 8; vi++) {
@@ -1334,7 +1425,12 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 			} else {
 				{
 					ProfScope ps(stream, mode, 0);
-					amd_quant_kernel<<<warp_grid, kWarps * 32, kWarps * sizeof(QuantScratch), stream>>>(p);
+					if (mode == 4 || mode == 5) {
+						const unsigned per_cta = kWarps * (mode == 4 ? 2u : 4u);
+						amd_quant_dual_kernel<<<(p.n_blocks + per_cta - 1) / per_cta, kWarps * 32, kWarps * sizeof(DualQuantScratch), stream>>>(p);
+					} else {
+						amd_quant_kernel<<<warp_grid, kWarps * 32, kWarps * sizeof(QuantScratch), stream>>>(p);
+					}
 				}
 				if (mode != 7) {
 					ProfScope ps(stream, mode, 1);
@@ -1342,7 +1438,7 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 				}
 				{
 					ProfScope ps(stream, mode, 2);
-					amd_window_kernel<<<window_grid, kWarps * 32, kWarps * sizeof(WindowScratch), stream>>>(p);
+					amd_window_kernel<<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch), stream>>>(p);
 				}
 				launches += mode != 7 ? 3 : 2;
 			}

@@ -237,15 +237,41 @@ A7_HDN void dominant_axis(const real cov[4][4], real axis[4], int dim) {
 // working on another subset of the same block -- hit 16 different bank pairs or broadcast) and keeps its two
 // n-element FP64 work arrays in caller-provided storage: lane-strided shared memory on the GPU (element k at
 // [k * stride]: conflict-free, no local-memory traffic), plain local arrays on the host.
-struct QuantIO {
+struct QuantIO { // generic pointers: host build and the thread-per-block kernel (local work arrays)
 	const real *px;   // px[channel * 16 + texel], 0..255
 	uint64_t texels;  // 4 bits per entry: texel of entry k
 	uint32_t chan;    // 2 bits per component: source channel of component j
 	real *proj, *dev; // work arrays
 	int stride;
+	A7_HD real point(uint32_t idx) const { return px[idx]; }
+	A7_HD real get_proj(int i) const { return proj[i * stride]; }
+	A7_HD void set_proj(int i, real v) const { proj[i * stride] = v; }
+	A7_HD real get_dev(int i) const { return dev[i * stride]; }
+	A7_HD void set_dev(int i, real v) const { dev[i * stride] = v; }
 };
-A7_HD real quant_point(const QuantIO &io, int k, int j) {
-	return io.px[((io.chan >> (2 * j)) & 3u) * 16u + (uint32_t) ((io.texels >> (4 * k)) & 15u)];
+#if defined(__CUDACC__)
+// The same three arrays in SHARED memory, named by 32-bit shared-window addresses and touched with ld.shared / st.shared:
+// the warp kernels' quantiser then issues LDS / STS with 32-bit address arithmetic instead of generic 64-bit loads.
+struct QuantIOShared {
+	uint32_t px, proj, dev; // byte addresses in the shared window (__cvta_generic_to_shared)
+	uint64_t texels;
+	uint32_t chan;
+	int stride;             // elements between consecutive entries of proj / dev
+	static __device__ __forceinline__ real lds(uint32_t a) {
+		real v;
+		asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+		return v;
+	}
+	static __device__ __forceinline__ void sts(uint32_t a, real v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+	__device__ __forceinline__ real point(uint32_t idx) const { return lds(px + idx * 8u); }
+	__device__ __forceinline__ real get_proj(int i) const { return lds(proj + (uint32_t) (i * stride) * 8u); }
+	__device__ __forceinline__ void set_proj(int i, real v) const { sts(proj + (uint32_t) (i * stride) * 8u, v); }
+	__device__ __forceinline__ real get_dev(int i) const { return lds(dev + (uint32_t) (i * stride) * 8u); }
+	__device__ __forceinline__ void set_dev(int i, real v) const { sts(dev + (uint32_t) (i * stride) * 8u, v); }
+};
+#endif
+template <class IO> A7_HD real quant_point(const IO &io, int k, int j) {
+	return io.point(((io.chan >> (2 * j)) & 3u) * 16u + (uint32_t) ((io.texels >> (4 * k)) & 15u));
 }
 A7_HD uint64_t texels_of_mask(uint32_t mask16, int &n) { // entries in texel order
 	uint64_t t = 0;
@@ -259,14 +285,13 @@ A7_HD uint64_t texels_of_mask(uint32_t mask16, int &n) { // entries in texel ord
 	return t;
 }
 
-// quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of the n scalars io.proj[] (lattice A_n* decoding).
+// quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of the n scalars of io's proj array (lattice A_n* decoding).
 // Returns the indices packed 4 bits per entry (values taken & 15 like every consumer does).
-A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
-	const int st = io.stride;
-	real m = io.proj[0], M = m;
+template <class IO> A7_HDN uint64_t lattice_quantise(const IO &io, int k, int n) {
+	real m = io.get_proj(0), M = m;
 #pragma unroll 1
 	for (int i = 1; i < n; i++) {
-		const real v = io.proj[i * st];
+		const real v = io.get_proj(i);
 		m = m < v ? m : v;
 		M = M > v ? M : v;
 	}
@@ -276,11 +301,11 @@ A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
 	uint64_t z4 = 0; // floor values, one nibble each (0 .. k-1)
 #pragma unroll 1
 	for (int i = 0; i < n; i++) {
-		const real v = io.proj[i * st] * s;
+		const real v = io.get_proj(i) * s;
 		const real z = floor(v + 0.5 - m * s);
 		z4 |= (uint64_t) ((int) z & 15) << (4 * i);
 		const real d = v - z - m * s;
-		io.dev[i * st] = d;
+		io.set_dev(i, d);
 		dm += d;
 		r += d * d;
 	}
@@ -288,7 +313,7 @@ A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
 	if ((real) n * r - dm * dm >= (real) (n - 1) / 4 / 2) {
 		dm /= (real) n;
 #pragma unroll 1
-		for (int i = 0; i < n; i++) io.dev[i * st] -= dm;
+		for (int i = 0; i < n; i++) io.set_dev(i, io.get_dev(i) - dm);
 		// stable rank of every deviation (what an insertion sort with the comparator `a - b > 0` produces)
 		// stable rank of every deviation (what an insertion sort with the comparator `a - b > 0` produces), one compare
 		// per PAIR: for i < j exactly one of the two gains a rank -- entry i if d_i > d_j, else entry j (a - b > 0 is
@@ -296,9 +321,9 @@ A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
 		uint64_t rank4 = 0;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
-			const real ki = io.dev[i * st];
+			const real ki = io.get_dev(i);
 #pragma unroll 1
-			for (int j = i + 1; j < n; j++) rank4 += 1ull << (4 * (ki > io.dev[j * st] ? i : j));
+			for (int j = i + 1; j < n; j++) rank4 += 1ull << (4 * (ki > io.get_dev(j) ? i : j));
 		}
 		uint64_t ord = 0;
 #pragma unroll 1
@@ -307,7 +332,7 @@ A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
 		int j = -1;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
-			l += io.dev[(int) ((ord >> (4 * i)) & 15u) * st] - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
+			l += io.get_dev((int) ((ord >> (4 * i)) & 15u)) - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
 			if (l < mm) { mm = l; j = i; }
 		}
 		j = (j + 1) % n;
@@ -331,7 +356,7 @@ A7_HDN uint64_t lattice_quantise(const QuantIO &io, int k, int n) {
 }
 
 // refit (:1923-1956): direction through the index-weighted centred points, projections into io.proj; s, t out
-template <int DIM> A7_HD void quant_refit(const QuantIO &io, const real *mean, int n, uint64_t a, bool want_st, real &s, real &t) {
+template <int DIM, class IO> A7_HD void quant_refit(const IO &io, const real *mean, int n, uint64_t a, bool want_st, real &s, real &t) {
 	real dir[DIM], q = 0;
 	real ss = 0, tt = 0;
 #pragma unroll
@@ -361,7 +386,7 @@ template <int DIM> A7_HD void quant_refit(const QuantIO &io, const real *mean, i
 		real p = 0;
 #pragma unroll
 		for (int j = 0; j < DIM; j++) p += (quant_point(io, k, j) - mean[j]) * dir[j];
-		io.proj[k * io.stride] = p;
+		io.set_proj(k, p);
 	}
 	s = ss;
 	t = tt;
@@ -369,10 +394,9 @@ template <int DIM> A7_HD void quant_refit(const QuantIO &io, const real *mean, i
 
 // optQuantAnD_d (:1874-2045): PCA line + iterative optimal uniform quantiser over the n points of `io`.
 // Returns the SSE; index_out = final indices, 4 bits per entry.
-template <int DIM> A7_HD real quantise_points(const QuantIO &io, int n, int clusters, uint64_t &index_out) {
+template <int DIM, class IO> A7_HD real quantise_points(const IO &io, int n, int clusters, uint64_t &index_out) {
 	index_out = 0;
 	if (n == 0) return 0;
-	const int st = io.stride;
 	real mean[DIM];
 #pragma unroll
 	for (int j = 0; j < DIM; j++) mean[j] = 0;
@@ -413,7 +437,7 @@ template <int DIM> A7_HD real quantise_points(const QuantIO &io, int n, int clus
 			real p = 0;
 #pragma unroll
 			for (int j = 0; j < DIM; j++) p += (quant_point(io, k, j) - mean[j]) * dir[j];
-			io.proj[k * st] = p;
+			io.set_proj(k, p);
 		}
 	}
 	// The loop below is the reference's (:1911-2007), including its quirks: the convergence test compares against
@@ -467,7 +491,7 @@ template <int DIM> A7_HD real quantise_points(const QuantIO &io, int n, int clus
 				for (int c = 0; c < clusters - 1; c++) {
 					const real bound = ((real) c + 0.5 - s) * t;
 #pragma unroll 1
-					for (int j = 0; j < n; j++) b += (uint64_t) (io.proj[j * st] > bound ? 1 : 0) << (4 * j);
+					for (int j = 0; j < n; j++) b += (uint64_t) (io.get_proj(j) > bound ? 1 : 0) << (4 * j);
 				}
 				slot = memo_next;
 				memo_next = (memo_next + 1) & 3;
@@ -551,7 +575,7 @@ template <int DIM> A7_HD real quantise_points(const QuantIO &io, int n, int clus
 	index_out = cur;
 	return err;
 }
-A7_HDN real quantise_subset(const QuantIO &io, int n, int clusters, int dim, uint64_t &index_out) {
+template <class IO> A7_HDN real quantise_subset(const IO &io, int n, int clusters, int dim, uint64_t &index_out) {
 	return dim == 3 ? quantise_points<3>(io, n, clusters, index_out) : quantise_points<4>(io, n, clusters, index_out);
 }
 

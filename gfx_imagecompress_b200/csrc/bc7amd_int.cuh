@@ -941,21 +941,23 @@ A7_HD void window_planes_u8(const uint32_t *d, int n, uint32_t plane[16]) {
 			plane[j * 4 + w] = v;
 		}
 }
+// The work item in three steps, so that the CUDA window kernel can run the middle one with a lane per (item, channel,
+// parity combination) instead of a lane per item:
+//   window_item_fit_u8     least-squares endpoints, byte-permute selectors
+//   window_sub_search_u8   one channel, one (pp0, pp1): lattice floors of the two endpoints, the (p1, p2) window around them,
+//                          first minimum in scan order
+//   window_item_combine    sum over the channels per parity vector, first minimum (:975-1000)
+// epa[i * 4 + j] = least-squares endpoint i of channel j
 template <int CLOG>
-A7_HDN uint32_t window_item_lut_u8(const uint32_t *lut, const uint32_t *d, const uint32_t *plane, int n, uint64_t collapsed, int q, int p, int size,
-																	 int bits_total, int dim, uint64_t &epo_out) {
-	constexpr int C = 1 << CLOG;
-	static_assert(C <= 8, "one 64-bit ramp");
-	const int type = bits_total % (2 * dim);
-	const int use_par = type != 0;
-	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
+A7_HD void window_item_fit_u8(const uint32_t *d, int n, uint64_t collapsed, int q, int p, int dim, real epa_out[8], uint32_t sel[4]) {
 	ClusterAcc<CLOG> cs;
 	cluster_acc<CLOG>(d, n, collapsed, q, p, cs);
-	real epa[2][4];
+	real epa[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 	fit_endpoints_acc<CLOG>(cs, dim, epa);
-	const int nw = (n + 3) >> 2;
-	const uint32_t last = (n & 3) ? ((1u << (8 * (n & 3))) - 1u) : 0xffffffffu;
-	uint32_t sel[4];
+#pragma unroll
+	for (int i = 0; i < 2; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) epa_out[i * 4 + j] = epa[i][j];
 #pragma unroll
 	for (int w = 0; w < 4; w++) {
 		uint32_t sw = 0;
@@ -967,52 +969,47 @@ A7_HDN uint32_t window_item_lut_u8(const uint32_t *lut, const uint32_t *d, const
 		}
 		sel[w] = sw;
 	}
-	int ed[2][2][4], ep2[2][2][2][4];
-	const int rr = use_par ? 2 : 1, step = 1 << use_par, top = (1 << mb) - 1;
-#pragma unroll 1
-	for (int j = 0; j < dim; j++) {
-		const uint32_t plw[4] = {plane[4 * j], plane[4 * j + 1], plane[4 * j + 2], plane[4 * j + 3]};
-		int fl[2][2];
+}
+// returns best error << 16 | p1 << 8 | p2
+template <int CLOG>
+A7_HD uint64_t window_sub_search_u8(const uint32_t *lut, real ep0, real ep1, const uint32_t sel[4], const uint32_t plw[4], int n, int mb, int use_par,
+																	int size, int pp0, int pp1) {
+	constexpr int C = 1 << CLOG;
+	static_assert(C <= 8, "one 64-bit ramp");
+	const int nw = (n + 3) >> 2;
+	const uint32_t last = (n & 3) ? ((1u << (8 * (n & 3))) - 1u) : 0xffffffffu;
+	const int step = 1 << use_par, top = (1 << mb) - 1;
+	int lo[2], hi[2];
 #pragma unroll
-		for (int i = 0; i < 2; i++)
-#pragma unroll
-			for (int par = 0; par < 2; par++) fl[i][par] = par < rr ? endpoint_floor_int(epa[i][j], mb, use_par, par) : 0;
-#pragma unroll 1
-		for (int pp0 = 0; pp0 < rr; pp0++)
-#pragma unroll 1
-			for (int pp1 = 0; pp1 < rr; pp1++) {
-				int lo[2], hi[2];
-#pragma unroll
-				for (int i = 0; i < 2; i++) {
-					const int pi = i ? pp1 : pp0;
-					const int f = pi ? fl[i][1] : fl[i][0];
-					lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
-					hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
-				}
-				int best = INT32_MAX, b1 = 0, b2 = 0;
-#pragma unroll 1
-				for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
-					const int e1 = expand_bits(mb, p1);
-#pragma unroll 1
-					for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
-						const int e2 = expand_bits(mb, p2);
-						const uint32_t r0 = ramp_lut_word<CLOG>(lut, e1, e2, 0), r1 = C > 4 ? ramp_lut_word<CLOG>(lut, e1, e2, C > 4 ? 1 : 0) : 0u;
-						uint32_t t = 0;
-#pragma unroll
-						for (int w = 0; w < 4; w++) { // (static indices: sel[] and the plane words stay in registers)
-							if (w >= nw) break;
-							uint32_t ad = vabsdiff4_u8(perm_bytes(r0, r1, sel[w]), plw[w]);
-							if (w == nw - 1) ad &= last;
-							t = dot4_u8(ad, ad, t);
-						}
-						if ((int) t < best) { best = (int) t; b1 = p1; b2 = p2; }
-					}
-				}
-				ed[pp0][pp1][j] = best;
-				ep2[pp0][pp1][0][j] = b1;
-				ep2[pp0][pp1][1][j] = b2;
-			}
+	for (int i = 0; i < 2; i++) {
+		const int f = endpoint_floor_int(i ? ep1 : ep0, mb, use_par, i ? pp1 : pp0);
+		lo[i] = f - ((f < (size >> 1) - 1 ? f : (size >> 1) - 1) & ~use_par);
+		hi[i] = f + ((top - f < (size >> 1) ? top - f : (size >> 1)) & ~use_par);
 	}
+	uint32_t best = 0x7fffffffu;
+	int b1 = 0, b2 = 0;
+#pragma unroll 1
+	for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
+		const int e1 = expand_bits(mb, p1);
+#pragma unroll 1
+		for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
+			const int e2 = expand_bits(mb, p2);
+			const uint32_t r0 = ramp_lut_word<CLOG>(lut, e1, e2, 0), r1 = C > 4 ? ramp_lut_word<CLOG>(lut, e1, e2, C > 4 ? 1 : 0) : 0u;
+			uint32_t t = 0;
+#pragma unroll
+			for (int w = 0; w < 4; w++) { // (static indices: the selectors and the plane words stay in registers)
+				if (w >= nw) break;
+				uint32_t ad = vabsdiff4_u8(perm_bytes(r0, r1, sel[w]), plw[w]);
+				if (w == nw - 1) ad &= last;
+				t = dot4_u8(ad, ad, t);
+			}
+			if (t < best) { best = t; b1 = p1; b2 = p2; }
+		}
+	}
+	return ((uint64_t) best << 16) | ((uint64_t) (b1 & 255) << 8) | (uint64_t) (b2 & 255);
+}
+// res[j * 4 + pp0 * 2 + pp1] from window_sub_search_u8 (SAME_PAR never reads the mixed-parity entries)
+A7_HD uint32_t window_item_combine(const uint64_t *res, int type, int dim, uint64_t &epo_out) {
 	int64_t err_1 = INT64_MAX;
 	int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll 1
@@ -1020,15 +1017,42 @@ A7_HDN uint32_t window_item_lut_u8(const uint32_t *lut, const uint32_t *d, const
 		const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
 		int64_t e2 = 0;
 #pragma unroll 1
-		for (int j = 0; j < dim; j++) e2 += ed[v0][v1][j];
+		for (int j = 0; j < dim; j++) e2 += (int64_t) (res[j * 4 + v0 * 2 + v1] >> 16);
 		if (e2 < err_1) {
 			err_1 = e2;
 #pragma unroll 1
-			for (int j = 0; j < dim; j++) { epo_1[0][j] = ep2[v0][v1][0][j]; epo_1[1][j] = ep2[v0][v1][1][j]; }
+			for (int j = 0; j < dim; j++) {
+				const uint64_t r = res[j * 4 + v0 * 2 + v1];
+				epo_1[0][j] = (int) ((r >> 8) & 255u);
+				epo_1[1][j] = (int) (r & 255u);
+			}
 		}
 	}
 	epo_out = pack_ep8(epo_1);
 	return (uint32_t) err_1;
+}
+// the three steps run by one caller (host build / test)
+template <int CLOG>
+A7_HDN uint32_t window_item_lut_u8(const uint32_t *lut, const uint32_t *d, const uint32_t *plane, int n, uint64_t collapsed, int q, int p, int size,
+																	 int bits_total, int dim, uint64_t &epo_out) {
+	const int type = bits_total % (2 * dim);
+	const int use_par = type != 0;
+	const int mb = (bits_total + 2 * dim - 1) / (2 * dim);
+	real epa[8];
+	uint32_t sel[4];
+	window_item_fit_u8<CLOG>(d, n, collapsed, q, p, dim, epa, sel);
+	uint64_t res[16];
+#pragma unroll 1
+	for (int j = 0; j < dim; j++)
+#pragma unroll 1
+		for (int pp0 = 0; pp0 <= use_par; pp0++)
+#pragma unroll 1
+			for (int pp1 = 0; pp1 <= use_par; pp1++) {
+				if (type == SAME_PAR && pp0 != pp1) continue; // (the reference searches these too, nobody reads them)
+				const uint32_t plw[4] = {plane[4 * j], plane[4 * j + 1], plane[4 * j + 2], plane[4 * j + 3]};
+				res[j * 4 + pp0 * 2 + pp1] = window_sub_search_u8<CLOG>(lut, epa[j], epa[4 + j], sel, plw, n, mb, use_par, size, pp0, pp1);
+			}
+	return window_item_combine(res, type, dim, epo_out);
 }
 
 // Re-clustering against chosen endpoints (:1003-1030): packed palette, 4 native instructions per (texel, entry)

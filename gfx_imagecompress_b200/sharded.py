@@ -92,18 +92,6 @@ def encode_batch_sharded(codec: int, images: Sequence, fmt: int, rank: int, worl
 
 
 def box_mips(top):
-    """Box-filtered mip chain of an (H, W, C) uint8 tensor down to 1x1 (torch, device side).  Input preparation for the
-    batch workload; the reference leaves mip generation to its callers."""
-    import torch
-    chain = [top.contiguous()]
-    cur = top.to(torch.float32)
-    while cur.shape[0] > 1 or cur.shape[1] > 1:
-        h, w = cur.shape[0], cur.shape[1]
-        nh, nw = max(1, h // 2), max(1, w // 2)
-        cur = cur[:nh * 2 if h > 1 else 1, :nw * 2 if w > 1 else 1]
-        if h > 1:
-            cur = (cur[0::2] + cur[1::2]) * 0.5
-        if w > 1:
-            cur = (cur[:, 0::2] + cur[:, 1::2]) * 0.5
-        chain.append(torch.floor(cur + 0.5).clamp(0, 255).to(torch.uint8).contiguous())
-    return chain
+    """Box-filtered mip chain of an (H, W, 4) uint8 CUDA tensor down to 1x1 (b200ic_box_mip_rgba8_device).  Input preparation
+    for the batch workload; the reference leaves mip generation to its callers."""
+    return api.box_mip_chain(top.contiguous())

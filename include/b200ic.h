@@ -160,6 +160,16 @@ B200IC_API uint64_t b200ic_plan_shards(const uint32_t *widths, const uint32_t *h
 B200IC_API int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint64_t n_images,
 																					const b200ic_shard *shards, uint64_t n_shards, const b200ic_opts *opts, void *stream);
 
+/* ---- either side of the encode ------------------------------------------------------------------------
+ * Next mip level of a device-resident RGBA8 image: 2x2 box filter, floor(x + 0.5) rounding, dimensions floor(size / 2)
+ * (a dimension that is already 1 stays 1).  d_dst holds max(1, width/2) x max(1, height/2) texels.  Asynchronous. */
+B200IC_API int b200ic_box_mip_rgba8_device(const void *d_src, uint32_t width, uint32_t height, uint64_t src_pitch_bytes,
+																					 void *d_dst, uint64_t dst_pitch_bytes, void *stream);
+/* Writes a .dds file (DX10 header) with `levels` mip levels of host-resident blocks, level l being
+ * max(1, width >> l) x max(1, height >> l) texels.  The reference leaves file output to the external gfx_imageio. */
+B200IC_API int b200ic_write_dds(const char *path, int codec, int srgb, int is_signed, uint32_t width, uint32_t height,
+																uint32_t levels, const void *const *level_blocks);
+
 /* Per-kernel timing of the AMD BC7 pipeline (bench.py's roofline): while enabled, every kernel launch is bracketed by
  * CUDA events on the launching stream.  b200ic_profile_read waits for the recorded events, adds their durations (ms)
  * and counts into ms[mode * 4 + kind] / launches[mode * 4 + kind] (32 entries each; kind 0 quantise, 1 cube, 2 window,
