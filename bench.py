@@ -274,9 +274,10 @@ class ImageApi:
         return out
 
 
-def amd_profile(g, nblocks, sm_mhz, peaks):
+def amd_profile(g, nblocks, steps, sm_mhz, peaks):
     """Reads the per-kernel event times recorded by the library (b200ic_profile) and builds the roofline of the dominant
-    launch from the ncu instruction / DRAM counts of the same kernel (profiles/ncu_counters.json)."""
+    kernel from the ncu instruction / DRAM counts of the same kernel (profiles/ncu_counters.json).  An encode runs the 21
+    kernels of AMD_LAUNCHES once per chunk of <= 2^19 blocks; both sides are summed over the chunks of one image."""
     L = g.library()
     ms = (C.c_double * 32)()
     cnt = (C.c_uint64 * 32)()
@@ -286,8 +287,8 @@ def amd_profile(g, nblocks, sm_mhz, peaks):
         return None, None
     total = sum(v[0] for v in per.values())
     (m, k), (t, n) = max(per.items(), key=lambda kv: kv[1][0])
-    avg_ms = t / n
-    table = [{"kernel": KIND[kk], "mode": mm, "ms_per_launch": v[0] / v[1], "launches": v[1], "share": v[0] / total}
+    ms_per_image = t / steps
+    table = [{"kernel": KIND[kk], "mode": mm, "ms_per_step": v[0] / steps, "launches_per_step": v[1] // steps, "share": v[0] / total}
              for (mm, kk), v in sorted(per.items(), key=lambda kv: -kv[1][0])]
     ctr = _counters("bc7_amd")
     roof = None
@@ -296,18 +297,20 @@ def amd_profile(g, nblocks, sm_mhz, peaks):
         scale = nblocks / ctr["blocks"]
         lane_ops = pl["thread_inst"] * scale
         peak = _alu_peak(sm_mhz)
-        ach = lane_ops / (avg_ms / 1e3)
+        ach = lane_ops / (ms_per_image / 1e3)
         alg = nblocks * 80 + (nblocks * 584 if k != 3 else 0)  # texels + block (+ the phase kernels' hand-over words)
         roof = {"bound": "alu", "kernel": f"{KIND[k]} (mode {m})", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T lane-ops/s",
-                "frac": ach / peak, "traffic": pl["dram_bytes"] * scale, "ms_per_launch": avg_ms, "launches_timed": n,
-                "share_of_step": t / total, "lane_ops_per_launch": lane_ops, "lanes_per_inst": pl["thread_inst"] / max(pl["warp_inst"], 1.0),
+                "frac": ach / peak, "traffic": pl["dram_bytes"] * scale, "ms_per_launch": t / n, "launches_per_step": n // steps,
+                "ms_per_step": ms_per_image, "share_of_step": t / total, "lane_ops_per_step": lane_ops,
+                "lanes_per_inst": pl["thread_inst"] / max(pl["warp_inst"], 1.0),
                 "peak_source": "148 SMs x 128 FP32/INT32 lanes x median SM clock sampled during the timed region",
                 "counters": "profiles/ncu_counters/" + ctr["report"],
-                "hbm": {"achieved": alg / (avg_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": alg / (avg_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": alg},
+                "hbm": {"achieved": alg / (ms_per_image / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": alg / (ms_per_image / 1e3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_step": alg},
                 "note": "duration = CUDA events around this kernel's launches on the launching stream inside the timed steps "
-                        "(b200ic_profile); lane-ops / DRAM bytes = ncu counts of the same kernel on the same workload shape, "
-                        "scaled by blocks. The search is ALU bound (SURVEY.md 8d): the HBM fraction is the evidence, not the target"}
+                        "(b200ic_profile), summed over the chunks of one image; lane-ops / DRAM bytes = ncu counts of the same kernel "
+                        "on the same workload, summed the same way. The search is ALU bound (SURVEY.md 8d): the HBM fraction is "
+                        "the evidence, not the target"}
     return roof, table
 
 
@@ -359,7 +362,7 @@ def run_single_gpu(g, torch, dev, codec, size, steps, warmup, cpu_budget, with_c
         torch.cuda.synchronize()
         launches = g.launch_count() - n0
         if codec != 7:  # sub-10 ms kernels: keep the sampler alive long enough for >= 10 clock samples under load
-            t_end = time.perf_counter() + 1.2
+            t_end = time.perf_counter() + 2.5
             while time.perf_counter() < t_end:
                 step_device()
             torch.cuda.synchronize()
@@ -369,7 +372,7 @@ def run_single_gpu(g, torch, dev, codec, size, steps, warmup, cpu_budget, with_c
     peaks, how = _peaks()
     alg_bytes = in_bytes + nblocks * bb
     if codec == 7:
-        roof, table = amd_profile(g, nblocks, clk.get("sm_mhz"), peaks)
+        roof, table = amd_profile(g, nblocks, steps, clk.get("sm_mhz"), peaks)
     else:
         roof, table = single_kernel_roofline(cname, nblocks, sum(per_ms) / len(per_ms), alg_bytes, clk.get("sm_mhz"), peaks, how), None
     gpu_blocks = d_dst.cpu().numpy()

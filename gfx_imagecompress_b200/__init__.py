@@ -12,6 +12,6 @@ from .api import (  # noqa: F401
     Image_CompressRichGel999BC7, ImageCompress_Compress,
     Image_CompressAMDAlphaSingleModeBlock, Image_CompressAMDBC1Block, Image_CompressAMDMultiModeLDRBlock,
     Image_CompressRichGel999BC7enc16, Image_CompressAMDRGBSingleModeBlock, Image_CompressAMDExplictAlphaSingleModeBlock,
-    ImageCompress_PickCompressionType, device_count, set_devices, box_mip_chain, write_dds,
+    ImageCompress_PickCompressionType, device_count, set_devices, box_mip_chain, write_dds, decode_device,
 )
 from . import synth  # noqa: F401

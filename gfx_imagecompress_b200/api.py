@@ -90,6 +90,7 @@ def load_library(path: str | None = None):
     L.b200ic_set_devices.argtypes = [C.c_int]
     L.b200ic_device_count.restype = C.c_int
     L.b200ic_box_mip_rgba8_device.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.b200ic_decode_device.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
     L.b200ic_write_dds.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     L.b200ic_encode_blocks.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     L.b200ic_plan_shards.restype = C.c_uint64
@@ -234,6 +235,20 @@ def box_mip_chain(top, stream=None):
             _check(L.b200ic_box_mip_rgba8_device(s.data_ptr(), w, h, 0, d.data_ptr(), 0, st), "b200ic_box_mip_rgba8_device")
             chain.append(d)
     return chain
+
+
+def decode_device(codec: int, blocks, width: int, height: int, slices: int = 1, is_signed: bool = False, stream=None):
+    """b200ic_decode_device: `blocks` = CUDA uint8 tensor (nblocks, blockBytes). Returns (slices*height, width, C) texels:
+    uint8 RGBA / R / RG, or float16 RGBA for BC6H."""
+    import torch
+    assert blocks.is_cuda and blocks.is_contiguous()
+    ch = {BC4: 1, BC5: 2}.get(codec, 4)
+    out = torch.empty((slices * height, width, ch), dtype=torch.float16 if codec == BC6H else torch.uint8, device=blocks.device)
+    st = stream if stream is not None else torch.cuda.current_stream(blocks.device).cuda_stream
+    with torch.cuda.device(blocks.device):
+        _check(library().b200ic_decode_device(codec, blocks.data_ptr(), width, height, slices, int(is_signed), out.data_ptr(), 0, st),
+               "b200ic_decode_device")
+    return out
 
 
 def write_dds(path: str, codec: int, width: int, height: int, levels, srgb: bool = False, is_signed: bool = False) -> None:

@@ -26,6 +26,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hi
 UNITS = [
     ("api.cu", []),
     ("container.cu", []),
+    ("decode.cu", []),
     ("bc45.cu", ["--fmad=false"]),
     ("bc1.cu", ["--fmad=false"]),
     ("bc7rg.cu", ["--fmad=false"]),

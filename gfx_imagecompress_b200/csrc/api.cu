@@ -586,6 +586,22 @@ int b200ic_box_mip_rgba8_device(const void *d_src, uint32_t width, uint32_t heig
 	return 0;
 }
 
+int b200ic_decode_device(int codec, const void *d_blocks, uint32_t width, uint32_t height, uint32_t slices, int is_signed, void *d_dst,
+												 uint64_t dst_row_pitch_bytes, void *stream) {
+	t_error.clear();
+	if (!d_blocks || !d_dst) return fail("null buffer");
+	if (width == 0 || height == 0 || slices == 0) return fail("empty image");
+	const uint32_t bb = block_bytes(codec);
+	if (bb == 0 || codec == B200IC_BC23_COLOUR_HALF || codec == B200IC_BC2_ALPHA_HALF) return fail("unsupported codec");
+	const uint32_t tb = codec == B200IC_BC4 ? 1 : (codec == B200IC_BC5 ? 2 : (codec == B200IC_BC6H ? 8 : 4));
+	if (((uintptr_t) d_blocks % bb) || (tb >= 4 && (((uintptr_t) d_dst | dst_row_pitch_bytes) % tb))) return fail("misaligned buffer");
+	if (dst_row_pitch_bytes && dst_row_pitch_bytes < (uint64_t) width * tb) return fail("row pitch smaller than a row");
+	if (ensure_device()) return -1;
+	B200IC_CUDA(launch_decode(codec, d_blocks, width, height, slices, is_signed, d_dst, dst_row_pitch_bytes, static_cast<cudaStream_t>(stream)), "decode kernel launch");
+	g_launches.fetch_add(1, std::memory_order_relaxed);
+	return 0;
+}
+
 int b200ic_write_dds(const char *path, int codec, int srgb, int is_signed, uint32_t width, uint32_t height, uint32_t levels,
 										 const void *const *level_blocks) {
 	t_error.clear();

@@ -1345,6 +1345,13 @@ cudaError_t init_bc7amd_tables() {
 		e = cudaMemcpyToSymbol(c_qorder, order, sizeof(order));
 		if (e != cudaSuccess) return e;
 	}
+	{
+		double step[17 * 16] = {};
+		for (int n = 1; n <= 16; n++)
+			for (int i = 0; i < 16; i++) step[n * 16 + i] = (2. * (double) i + 1 - (double) n) / 2. / (double) n;
+		e = cudaMemcpyToSymbol(c_simplex_step, step, sizeof(step));
+		if (e != cudaSuccess) return e;
+	}
 	e = cudaFuncSetAttribute(amd_quant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(QuantScratch)));
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(amd_quant_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(DualQuantScratch)));

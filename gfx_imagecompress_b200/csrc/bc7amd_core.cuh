@@ -285,6 +285,17 @@ A7_HD uint64_t texels_of_mask(uint32_t mask16, int &n) { // entries in texel ord
 	return t;
 }
 
+// (2 i + 1 - n) / 2 / n of quant_AnD_Shell's move to the centre of the fundamental simplex (:1258-1259): one IEEE division
+// per entry on the host; on the GPU a 17 x 16 table of the same correctly rounded quotients (uploaded by
+// init_bc7amd_tables) instead of a 40-instruction FP64 division per entry and call.
+#if defined(__CUDACC__)
+static __constant__ double c_simplex_step[17 * 16];
+#endif
+#if defined(__CUDA_ARCH__)
+#define A7_SIMPLEX_STEP(n, i) c_simplex_step[(n) * 16 + (i)]
+#else
+#define A7_SIMPLEX_STEP(n, i) ((2. * (real) (i) + 1 - (real) (n)) / 2. / (real) (n))
+#endif
 // quant_AnD_Shell (:1201-1286): optimal uniform k-level quantisation of the n scalars of io's proj array (lattice A_n* decoding).
 // Returns the indices packed 4 bits per entry (values taken & 15 like every consumer does).
 template <class IO> A7_HDN uint64_t lattice_quantise(const IO &io, int k, int n) {
@@ -332,7 +343,7 @@ template <class IO> A7_HDN uint64_t lattice_quantise(const IO &io, int k, int n)
 		int j = -1;
 #pragma unroll 1
 		for (int i = 0; i < n; i++) {
-			l += io.get_dev((int) ((ord >> (4 * i)) & 15u)) - (2. * (real) i + 1 - (real) n) / 2. / (real) n;
+			l += io.get_dev((int) ((ord >> (4 * i)) & 15u)) - A7_SIMPLEX_STEP(n, i);
 			if (l < mm) { mm = l; j = i; }
 		}
 		j = (j + 1) % n;
@@ -591,7 +602,14 @@ A7_HD int endpoint_floor(real v, int bits, int use_par, int odd) {
 	return (i1 << use_par) + odd;
 }
 
-// index_collapse_ (:513-538); returns the new maximum index
+// index_collapse_ (:513-538); returns the new maximum index.
+// The reference keeps the LARGEST d in [2, max - min] that divides every index[k] - min (else 1): that is the gcd of the
+// differences (every common divisor divides the gcd, and the gcd does not exceed the largest difference).  Here: AND of
+// per-value divisor masks (bit d set when d divides v; v = 0: every d), highest common bit; the division by D <= 15 is a
+// multiply and shift.
+static B7T_QUAL uint16_t kDivisorMask[16] = {0xfffe, 0x0002, 0x0006, 0x000a, 0x0016, 0x0022, 0x004e, 0x0082,
+																						 0x0116, 0x020a, 0x0426, 0x0802, 0x105e, 0x2002, 0x4086, 0x802a};
+static B7T_QUAL uint16_t kInv12[16] = {0, 4096, 2048, 1366, 1024, 820, 683, 586, 512, 456, 410, 373, 342, 316, 293, 274}; // ceil(4096 / d)
 A7_HD int collapse_indices(int *index, int n) {
 	int mi = index[0], Mi = index[0];
 #pragma unroll 1
@@ -599,19 +617,18 @@ A7_HD int collapse_indices(int *index, int n) {
 		mi = mi < index[k] ? mi : index[k];
 		Mi = Mi > index[k] ? Mi : index[k];
 	}
+	uint32_t common = 0xfffeu;
+#pragma unroll 1
+	for (int k = 0; k < n; k++) common &= kDivisorMask[(index[k] - mi) & 15];
+	// divisors above the largest difference only survive when every difference is 0: D = 1 then (the loop of :520 is empty)
+	common &= (2u << (Mi - mi)) - 1u;
 	int D = 1;
-#pragma unroll 1
-	for (int d = 2; d <= Mi - mi; d++) {
-		int k = 0;
-#pragma unroll 1
-		for (; k < n; k++)
-			if ((index[k] - mi) % d != 0) break;
-		if (k >= n) D = d;
-	}
+	while (common >> (D + 1)) D++;
+	const uint32_t inv = kInv12[D];
 	int top = 0;
 #pragma unroll 1
 	for (int k = 0; k < n; k++) {
-		index[k] = (index[k] - mi) / D;
+		index[k] = (int) (((uint32_t) (index[k] - mi) * inv) >> 12); // exact for 0 <= x <= 15, 1 <= D <= 15
 		top = top > index[k] ? top : index[k];
 	}
 	return top;

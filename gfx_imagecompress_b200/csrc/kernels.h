@@ -16,6 +16,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 cudaError_t launch_bc6h(const SrcImage &img, const b200ic_opts &opts, void *dst, cudaStream_t stream);
 cudaError_t launch_box_mip_rgba8(const void *src, uint32_t sw, uint32_t sh, uint64_t spitch, void *dst, uint64_t dpitch, cudaStream_t stream);
 int write_dds(const char *path, int codec, int srgb, int is_signed, uint32_t width, uint32_t height, uint32_t levels, const void *const *level_blocks);
+cudaError_t launch_decode(int codec, const void *blocks, uint32_t width, uint32_t height, uint32_t slices, int is_signed, void *dst, uint64_t row_pitch,
+													cudaStream_t stream);
 void count_launches(int extra); // launchers issuing more than one kernel per encode report the extra ones
 cudaError_t init_bc7rg_tables();
 cudaError_t init_bc7amd_tables();

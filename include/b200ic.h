@@ -165,6 +165,12 @@ B200IC_API int b200ic_encode_batch_device(int codec, const b200ic_image_desc *im
  * (a dimension that is already 1 stays 1).  d_dst holds max(1, width/2) x max(1, height/2) texels.  Asynchronous. */
 B200IC_API int b200ic_box_mip_rgba8_device(const void *d_src, uint32_t width, uint32_t height, uint64_t src_pitch_bytes,
 																					 void *d_dst, uint64_t dst_pitch_bytes, void *stream);
+/* Decodes blocks (slices x blocksY x blocksX, row-major) back to texels: RGBA8 for BC1 / BC2 / BC3 / BC7, R8 for BC4,
+ * RG8 for BC5, RGBA16F (A = 1) for BC6H (`is_signed` selects the signed format).  The reference has no decoder; this
+ * follows the S3TC / RGTC / BPTC specifications.  d_dst: slices x height rows of `dst_row_pitch_bytes` (0 = tight).
+ * Asynchronous. */
+B200IC_API int b200ic_decode_device(int codec, const void *d_blocks, uint32_t width, uint32_t height, uint32_t slices, int is_signed,
+																		void *d_dst, uint64_t dst_row_pitch_bytes, void *stream);
 /* Writes a .dds file (DX10 header) with `levels` mip levels of host-resident blocks, level l being
  * max(1, width >> l) x max(1, height >> l) texels.  The reference leaves file output to the external gfx_imageio. */
 B200IC_API int b200ic_write_dds(const char *path, int codec, int srgb, int is_signed, uint32_t width, uint32_t height,

@@ -33,17 +33,18 @@ def same_or_within_tolerance(name, got, want, px, codec):
 
 
 def mip_tail(top):
-    """Box-filtered chain of an (H, W, C) uint8 image down to 1x1 (numpy twin of sharded.box_mips)."""
+    """Box-filtered chain of an (H, W, C) uint8 image down to 1x1, every level filtered from the previous (quantised)
+    level with floor(x + 0.5) rounding (numpy twin of b200ic_box_mip_rgba8_device)."""
     chain = [np.ascontiguousarray(top)]
-    cur = top.astype(np.float32)
-    while cur.shape[0] > 1 or cur.shape[1] > 1:
+    while chain[-1].shape[0] > 1 or chain[-1].shape[1] > 1:
+        cur = chain[-1].astype(np.float32)
         h, w = cur.shape[:2]
         if h > 1:
             cur = (cur[0:h // 2 * 2:2] + cur[1:h // 2 * 2:2]) * 0.5
         if w > 1:
             cur = (cur[:, 0:w // 2 * 2:2] + cur[:, 1:w // 2 * 2:2]) * 0.5
-        chain.append(np.floor(cur + 0.5).clip(0, 255).astype(np.uint8))
-    return [np.ascontiguousarray(c) for c in chain]
+        chain.append(np.ascontiguousarray(np.floor(cur + 0.5).clip(0, 255).astype(np.uint8)))
+    return chain
 
 
 @pytest.mark.gpu

@@ -20,6 +20,10 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "n
 def read(path):
     """`path` is the --csv --log-file of `ncu --metrics ...` (one row per launch and metric)."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0] != "ID" and not r[0].startswith("==")]
+    # tools/ncu_capture.py runs the encode twice (warm-up, then the one that counts): keep the second half of the launches
+    all_ids = sorted({int(r[0]) for r in rows})
+    keep = set(all_ids[len(all_ids) // 2:])
+    rows = [r for r in rows if int(r[0]) in keep]
     out = dict(launches=0, dram_bytes=0.0, warp_inst=0.0, thread_inst=0.0, time_s=0.0, kernels=[], per_launch={})
     ids = set()
     for r in rows:
@@ -61,8 +65,17 @@ def main(args):
         db[codec] = {"report": os.path.basename(rep), "blocks": b, "launches_per_encode": c["launches"], "kernels": c["kernels"],
                      "dram_bytes_per_block": c["dram_bytes"] / b, "warp_inst_per_block": c["warp_inst"] / b,
                      "thread_inst_per_block": c["thread_inst"] / b, "kernel_time_s_under_ncu": c["time_s"]}
-        if c["launches"] > 1:  # AMD BC7: one record per launch of the encode, in launch order (bench.py maps them to (mode, phase))
-            db[codec]["per_launch"] = c["per_launch"]
+        if c["launches"] > 1:
+            # AMD BC7: 21 launches per chunk of <= 2^19 blocks, in a fixed (mode, phase) order (bench.py AMD_LAUNCHES); the
+            # records of the chunks are folded into one total per (mode, phase) over the whole encode
+            pl = c["per_launch"]
+            if codec == "bc7_amd" and len(pl) % 21 == 0:
+                fold = []
+                for k in range(21):
+                    grp = pl[k::21]
+                    fold.append(dict(kernel=grp[0]["kernel"], launches=len(grp), **{m: sum(g[m] for g in grp) for m in ("dram_bytes", "warp_inst", "thread_inst", "time_s")}))
+                pl = fold
+            db[codec]["per_launch"] = pl
         print(codec, db[codec])
     json.dump(db, open(path, "w"), indent=1, sort_keys=True)
 
