@@ -697,8 +697,11 @@ int b200ic_encode_batch_device(int codec, const b200ic_image_desc *images, uint6
 		const uint32_t y0 = r0 * 4, y1 = r1 * 4 < im.height ? r1 * 4 : im.height;
 		const uint8_t *src = static_cast<const uint8_t *>(im.src) + (uint64_t) y0 * pitch;
 		uint8_t *dst = static_cast<uint8_t *>(im.dst) + (uint64_t) r0 * blocks_x * bb;
-		// big shards fill the GPU on their own and go to the caller's order on stream 0; small ones (low mips) overlap
-		rc = b200ic_encode_device(codec, src, im.format, im.width, y1 - y0, pitch, 0, 1, opts, dst, cx.streams[k % ring]);
+		// small shards (low mips) overlap on the ring; a shard that fills the GPU on its own keeps to one stream for AMD BC7,
+		// whose per-mode kernels slow each other down when launches of different modes share the SMs
+		const bool big = (uint64_t) blocks_x * (r1 - r0) >= 4096;
+		const int si = (codec == B200IC_BC7_AMD && big) ? 0 : (int) (k % ring);
+		rc = b200ic_encode_device(codec, src, im.format, im.width, y1 - y0, pitch, 0, 1, opts, dst, cx.streams[si]);
 	}
 	for (int i = 0; i < ring; i++) {
 		cudaEventRecord(cx.join[i], cx.streams[i]);
