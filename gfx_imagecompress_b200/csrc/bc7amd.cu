@@ -855,6 +855,67 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, co
 	}
 }
 
+// EncodeSingleIndexBlock (pack_single_index, bc7amd_core.cuh) spread over the warp: lane i < 16 = texel i (its index, the
+// anchor flip of its subset, its bit position by a prefix sum of the index widths), lanes 0 .. = the endpoint fields and
+// p-bits, lane 31 = mode and partition; the 128-bit block is the OR of the lanes' contributions.
+__device__ __forceinline__ void put128(uint64_t &lo, uint64_t &hi, uint32_t v, int n, int pos) {
+	if (n <= 0) return;
+	v &= (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
+	if (pos < 64) {
+		lo |= (uint64_t) v << pos;
+		if (pos + n > 64) hi |= (uint64_t) v >> (64 - pos);
+	} else {
+		hi |= (uint64_t) v << (pos - 64);
+	}
+}
+__device__ __forceinline__ void pack_single_index_warp(int mode, int partition, const ShakeOut *so, unsigned lane, uint64_t &out0, uint64_t &out1) {
+	const ModeInfo mi = mode_info(mode);
+	const int dim = mi.alpha == 0 ? 3 : 4, cbits = mi.alpha == 0 ? mi.vector_bits / 3 : mi.vector_bits / 4;
+	const int ib = mi.index_bits0, subsets = mi.subsets;
+	const int fix1 = subsets == 3 ? kBc7Anchor3a[partition] : (subsets == 2 ? kBc7Anchor2[partition] : 0);
+	const int fix2 = subsets == 3 ? kBc7Anchor3b[partition] : 0;
+	const int i = (int) lane & 15;
+	const int p = subset_of(subsets, partition, i);
+	const unsigned m0 = __ballot_sync(FULL, lane < 16 && p == 0), m1 = __ballot_sync(FULL, lane < 16 && p == 1), m2 = __ballot_sync(FULL, lane < 16 && p == 2);
+	const unsigned mine = p == 0 ? m0 : (p == 1 ? m1 : m2);
+	const int cnt = __popc(mine & ((1u << i) - 1u));
+	uint32_t blk = (uint32_t) ((so[p].idx >> (4 * cnt)) & 15u);
+	const int f0 = (int) ((__shfl_sync(FULL, blk, 0) >> (ib - 1)) & 1u), f1 = (int) ((__shfl_sync(FULL, blk, fix1) >> (ib - 1)) & 1u),
+						f2 = (int) ((__shfl_sync(FULL, blk, fix2) >> (ib - 1)) & 1u);
+	const int flip0 = f0, flip1 = subsets > 1 ? f1 : 0, flip2 = subsets > 2 ? f2 : 0;
+	if (p == 0 ? flip0 : (p == 1 ? flip1 : flip2)) blk = (uint32_t) ((1 << ib) - 1) - blk;
+	const int myfix = p == 0 ? 0 : (p == 1 ? fix1 : fix2);
+	const int width = lane < 16 ? ib - (i == myfix ? 1 : 0) : 0;
+	int incl = width;
+#pragma unroll
+	for (int d = 1; d < 16; d <<= 1) {
+		const int v = __shfl_up_sync(FULL, incl, d);
+		if ((int) lane >= d) incl += v;
+	}
+	const int header = mode + 1 + mi.partition_bits, nfields = dim * subsets * 2;
+	const int npb = mi.parity == SAME_PAR ? subsets : (mi.parity == BCC ? 2 * subsets : 0);
+	uint64_t lo = 0, hi = 0;
+	if (lane < 16) put128(lo, hi, blk, width, header + nfields * cbits + npb + incl - width);
+	if ((int) lane < nfields) { // endpoint field (channel k, subset s, endpoint e), stream order k, s, e
+		const int k = (int) lane / (subsets * 2), rem = (int) lane - k * subsets * 2, s = rem >> 1, e = rem & 1;
+		const int a = s == 0 ? flip0 : (s == 1 ? flip1 : flip2);
+		const uint32_t v = (so[s].ep[e ^ a] >> (8 * k)) & 255u;
+		put128(lo, hi, mi.parity != CART ? v >> 1 : v, cbits, header + (int) lane * cbits);
+	} else if ((int) lane < nfields + npb) { // p-bits; ONE_PBIT quirk: both from endpoint 1 after the flip (:443-448)
+		const int j = (int) lane - nfields, s = mi.parity == SAME_PAR ? j : (j >> 1), e = mi.parity == SAME_PAR ? 1 : (j & 1);
+		const int a = s == 0 ? flip0 : (s == 1 ? flip1 : flip2);
+		put128(lo, hi, so[s].ep[e ^ a] & 1u, 1, header + nfields * cbits + j);
+	}
+	if (lane == 31) {
+		put128(lo, hi, 1u << mode, mode + 1, 0);
+		put128(lo, hi, (uint32_t) partition, mi.partition_bits, mode + 1);
+	}
+	const uint32_t w0 = __reduce_or_sync(FULL, (uint32_t) lo), w1 = __reduce_or_sync(FULL, (uint32_t) (lo >> 32)),
+								 w2 = __reduce_or_sync(FULL, (uint32_t) hi), w3 = __reduce_or_sync(FULL, (uint32_t) (hi >> 32));
+	out0 = (uint64_t) w0 | ((uint64_t) w1 << 32);
+	out1 = (uint64_t) w2 | ((uint64_t) w3 << 32);
+}
+
 // One block of the window kernel
 __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3,
 																						 uint32_t block, unsigned lane) {
@@ -957,29 +1018,24 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 		ws.so[lane] = o;
 	}
 	__syncwarp();
+	int ba = 0, store = 0;
+	real be = A7_HUGE;
 	if (lane == 0) {
-		real be = A7_HUGE;
-		int ba = 0;
 		for (int a = 0; a < 8; a++) {
 			real e = 0;
 			for (int s = 0; s < subsets; s++) e += ws.so[a * subsets + s].err;
 			if (e < be) { be = e; ba = a; }
 		}
 		const real carried = p.first ? A7_HUGE : p.best_err[bc.gblock];
-		if (p.first || be < carried) {
-			SingleIndexResult r;
-			r.partition = ws.top[ba];
-			for (int s = 0; s < subsets; s++) {
-				const ShakeOut &o = ws.so[ba * subsets + s];
-				for (int k = 0; k < 4; k++) {
-					r.ep[s][0][k] = (int) ((o.ep[0] >> (8 * k)) & 255u);
-					r.ep[s][1][k] = (int) ((o.ep[1] >> (8 * k)) & 255u);
-				}
-				for (int i = 0; i < 16; i++) r.idx[s][i] = (int) ((o.idx >> (4 * i)) & 15u);
-			}
-			uint64_t blk[2];
-			pack_single_index(mode, r, blk);
-			p.dst[bc.gblock] = make_uint4((uint32_t) blk[0], (uint32_t) (blk[0] >> 32), (uint32_t) blk[1], (uint32_t) (blk[1] >> 32));
+		store = (p.first || be < carried) ? 1 : 0;
+	}
+	ba = __shfl_sync(FULL, ba, 0);
+	store = __shfl_sync(FULL, store, 0);
+	if (store) { // (uniform) this mode beats what the earlier modes left in dst
+		uint64_t b0, b1;
+		pack_single_index_warp(mode, ws.top[ba], &ws.so[ba * subsets], lane, b0, b1);
+		if (lane == 0) {
+			p.dst[bc.gblock] = make_uint4((uint32_t) b0, (uint32_t) (b0 >> 32), (uint32_t) b1, (uint32_t) (b1 >> 32));
 			p.best_err[bc.gblock] = be;
 		}
 	}

@@ -726,7 +726,24 @@ template <int CLOG> A7_HD uint32_t ramp_lut_word(const uint32_t *lut, int e1, in
 	constexpr int H = (1 << CLOG) / 4;
 	const int dl = e2 - e1;
 	const uint32_t rep = (uint32_t) e1 * 0x01010101u;
-	return dl < 0 ? rep - lut[256 * H + (-dl) * H + h] : rep + lut[dl * H + h];
+	const uint32_t v = lut[(dl < 0 ? (256 - dl) * H : dl * H) + h]; // (one load, no branch: the lanes of a warp mix both signs)
+	return dl < 0 ? rep - v : rep + v;
+}
+// the whole ramp (8 entries: both words with one 64-bit load; 4 entries: the high word is 0)
+template <int CLOG> A7_HD void ramp_lut_pair(const uint32_t *lut, int e1, int e2, uint32_t &r0, uint32_t &r1) {
+	constexpr int H = (1 << CLOG) / 4;
+	const int dl = e2 - e1;
+	const uint32_t rep = (uint32_t) e1 * 0x01010101u;
+	const int at = (dl < 0 ? (256 - dl) * H : dl * H);
+	if (H == 2) {
+		const uint64_t v = *reinterpret_cast<const uint64_t *>(lut + at); // (entries are pairs of words: 8-byte aligned)
+		r0 = dl < 0 ? rep - (uint32_t) v : rep + (uint32_t) v;
+		r1 = dl < 0 ? rep - (uint32_t) (v >> 32) : rep + (uint32_t) (v >> 32);
+	} else {
+		const uint32_t v = lut[at];
+		r0 = dl < 0 ? rep - v : rep + v;
+		r1 = 0;
+	}
 }
 // table-lookup form of cube_tab_word
 template <int CLOG> A7_HD uint32_t cube_tab_word_lut(const uint32_t *lut, const uint32_t ep[6], int bcc, int id) {
@@ -991,19 +1008,28 @@ A7_HD uint64_t window_sub_search_u8(const uint32_t *lut, real ep0, real ep1, con
 #pragma unroll 1
 	for (int p1 = lo[0]; p1 <= hi[0]; p1 += step) {
 		const int e1 = expand_bits(mb, p1);
+		// three candidates of the row at a time: their table loads are in flight together; compared in scan order
 #pragma unroll 1
-		for (int p2 = lo[1]; p2 <= hi[1]; p2 += step) {
-			const int e2 = expand_bits(mb, p2);
-			const uint32_t r0 = ramp_lut_word<CLOG>(lut, e1, e2, 0), r1 = C > 4 ? ramp_lut_word<CLOG>(lut, e1, e2, C > 4 ? 1 : 0) : 0u;
-			uint32_t t = 0;
+		for (int p2 = lo[1]; p2 <= hi[1]; p2 += 3 * step) {
+			uint32_t t[3];
 #pragma unroll
-			for (int w = 0; w < 4; w++) { // (static indices: the selectors and the plane words stay in registers)
-				if (w >= nw) break;
-				uint32_t ad = vabsdiff4_u8(perm_bytes(r0, r1, sel[w]), plw[w]);
-				if (w == nw - 1) ad &= last;
-				t = dot4_u8(ad, ad, t);
+			for (int u = 0; u < 3; u++) {
+				const int q2 = p2 + u * step;
+				uint32_t r0, r1;
+				ramp_lut_pair<CLOG>(lut, e1, expand_bits(mb, q2 <= hi[1] ? q2 : p2), r0, r1);
+				uint32_t tu = 0;
+#pragma unroll
+				for (int w = 0; w < 4; w++) { // (static indices: the selectors and the plane words stay in registers)
+					if (w >= nw) break;
+					uint32_t ad = vabsdiff4_u8(perm_bytes(r0, r1, sel[w]), plw[w]);
+					if (w == nw - 1) ad &= last;
+					tu = dot4_u8(ad, ad, tu);
+				}
+				t[u] = q2 <= hi[1] ? tu : 0xffffffffu;
 			}
-			if (t < best) { best = t; b1 = p1; b2 = p2; }
+#pragma unroll
+			for (int u = 0; u < 3; u++)
+				if (t[u] < best) { best = t[u]; b1 = p1; b2 = p2 + u * step; }
 		}
 	}
 	return ((uint64_t) best << 16) | ((uint64_t) (b1 & 255) << 8) | (uint64_t) (b2 & 255);
