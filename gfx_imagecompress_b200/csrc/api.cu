@@ -206,14 +206,14 @@ static int dispatch(int codec, const SrcImage &img, const b200ic_opts &o, void *
 	}
 	case B200IC_BC5: e = launch_bc45(img, 2, 0, d_dst, stream); break;
 	case B200IC_BC1:
-		if (o.amd_3d_refinement || o.amd_adaptive_weights) return fail("BC1: b3DRefinement / AdaptiveColourWeights are not supported");
+		if (o.amd_adaptive_weights) return fail("BC1: AdaptiveColourWeights is not supported (it reads uninitialised memory in the reference)");
 		e = launch_bc1(img, o, d_dst, stream);
 		break;
 	case B200IC_BC2:
 	case B200IC_BC3:
 	case B200IC_BC23_COLOUR_HALF:
 	case B200IC_BC2_ALPHA_HALF:
-		if (o.amd_3d_refinement || o.amd_adaptive_weights) return fail("BC2/BC3: b3DRefinement / AdaptiveColourWeights are not supported");
+		if (o.amd_adaptive_weights) return fail("BC2/BC3: AdaptiveColourWeights is not supported (it reads uninitialised memory in the reference)");
 		e = launch_bc23(img, o, codec == B200IC_BC3 ? kBc3Colour : (codec == B200IC_BC2 ? kBc2Both : (codec == B200IC_BC23_COLOUR_HALF ? kColourOnly : kAlphaOnly)),
 										d_dst, stream);
 		break;

@@ -122,7 +122,7 @@ cudaError_t launch_bc1(const SrcImage &img, const b200ic_opts &opts, void *dst, 
 	p.dst = static_cast<uint2 *>(dst);
 	p.n_blocks = (uint64_t) img.blocks_x * img.blocks_y * img.slices;
 	p.alpha_threshold = opts.bc1_alpha_threshold;
-	p.steps = opts.amd_refinement_steps;
+	p.steps = (opts.amd_refinement_steps & 0xff) | (opts.amd_3d_refinement ? bc1::kRefine3D : 0);
 	p.explicit_alpha = 0;
 	if (p.n_blocks == 0) return cudaSuccess;
 	const uint64_t grid = (2 * p.n_blocks + kThreads - 1) / kThreads;
@@ -139,7 +139,7 @@ cudaError_t launch_bc23(const SrcImage &img, const b200ic_opts &opts, int part, 
 	p.dst = static_cast<uint2 *>(dst);
 	p.n_blocks = (uint64_t) img.blocks_x * img.blocks_y * img.slices;
 	p.alpha_threshold = 0.0f;
-	p.steps = opts.amd_refinement_steps;
+	p.steps = (opts.amd_refinement_steps & 0xff) | (opts.amd_3d_refinement ? bc1::kRefine3D : 0);
 	p.explicit_alpha = part;
 	if (p.n_blocks == 0) return cudaSuccess;
 	if (part == kBc3Colour) {

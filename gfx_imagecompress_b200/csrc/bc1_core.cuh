@@ -37,6 +37,7 @@ B1_HD uint32_t fbits(float f) {
 
 // channel bit depths on the 5-6-5 grid, indexed by the internal channel order (B, G, R)
 B1_HD float grid_levels(int j) { return j == 1 ? 64.f : 32.f; } // 1 << bits
+constexpr int kRefine3D = 0x100; // flag in the `steps` argument: Refine3D instead of Refine (src/amd_bcx_body.cpp:1199-1202)
 B1_HD float grid_step(int j) { return j == 1 ? 4.f : 8.f; }     // 1 << (8 - bits)
 // channel weights: reference passes {0.3086 (R), 0.6094 (G), 0.0820 (B)}; internal order B, G, R
 B1_HD float chan_weight(int j) { return j == 0 ? 0.0820f : (j == 1 ? 0.6094f : 0.3086f); }
@@ -131,6 +132,86 @@ B1_HD float refine(float out[3][2], const float in[3][2], const float blk[16][3]
 	}
 	for (int j = 0; j < 3; j++)
 		for (int k = 0; k < 2; k++) out[j][k] = inp[j][k];
+	return best;
+}
+
+// Refine3D (:808-932, the b3DRefinement option): all six endpoint components jittered together, +-min(steps, 8) grid
+// steps each -- (2 steps + 1)^6 candidate ramps, G outermost, then B, then R (internal channels 1, 0, 2), each against
+// decompressor-exact ramps; first strict minimum in scan order.
+B1_HD float refine3d(float out[3][2], const float in[3][2], const float blk[16][3], const float *rpt, int n, int np, int steps) {
+	float rmp[3][5];
+	float inp0[3][2], inp[3][2], wk[3][2];
+	for (int k = 0; k < 2; k++)
+		for (int j = 0; j < 3; j++) inp0[j][k] = inp[j][k] = out[j][k] = in[j][k];
+	bool eq;
+	expand_endpoints(eq, wk, inp);
+	for (int j = 0; j < 3; j++) build_ramp(rmp[j], wk[j], np);
+	float best = 0.f; // ClstrErr (:203-246)
+	{
+		const int len = eq ? 1 : np;
+		for (int i = 0; i < n; i++) {
+			float shortest = 99999999999.f;
+			for (int r = 0; r < len; r++) {
+				const float d = (blk[i][2] - rmp[2][r]) * (blk[i][2] - rmp[2][r]) * chan_weight(2) +
+												(blk[i][1] - rmp[1][r]) * (blk[i][1] - rmp[1][r]) * chan_weight(1) +
+												(blk[i][0] - rmp[0][r]) * (blk[i][0] - rmp[0][r]) * chan_weight(0);
+				if (d < shortest) shortest = d;
+			}
+			best += shortest * rpt[i];
+		}
+	}
+	if (best == 0.f || !steps) return best;
+	const int span = steps < 8 ? steps : 8;
+	float err_g[4][16], err_gb[4][16];
+	for (int g0 = -span; g0 <= span; g0++) {
+		inp[1][0] = fmin_ref(fmax_ref(inp0[1][0] + (float) g0 * grid_step(1), 0.f), 255.f);
+		for (int g1 = -span; g1 <= span; g1++) {
+			inp[1][1] = fmin_ref(fmax_ref(inp0[1][1] + (float) g1 * grid_step(1), 0.f), 255.f);
+			expand_endpoints(eq, wk, inp);
+			build_ramp(rmp[1], wk[1], np);
+			for (int i = 0; i < n; i++)
+				for (int r = 0; r < np; r++) {
+					const float d = rmp[1][r] - blk[i][1];
+					err_g[r][i] = d * d * chan_weight(1);
+				}
+			for (int b0 = -span; b0 <= span; b0++) {
+				inp[0][0] = fmin_ref(fmax_ref(inp0[0][0] + (float) b0 * grid_step(0), 0.f), 255.f);
+				for (int b1 = -span; b1 <= span; b1++) {
+					inp[0][1] = fmin_ref(fmax_ref(inp0[0][1] + (float) b1 * grid_step(0), 0.f), 255.f);
+					expand_endpoints(eq, wk, inp);
+					build_ramp(rmp[0], wk[0], np);
+					for (int i = 0; i < n; i++)
+						for (int r = 0; r < np; r++) {
+							const float d = rmp[0][r] - blk[i][0];
+							err_gb[r][i] = err_g[r][i] + d * d * chan_weight(0);
+						}
+					for (int r0 = -span; r0 <= span; r0++) {
+						inp[2][0] = fmin_ref(fmax_ref(inp0[2][0] + (float) r0 * grid_step(2), 0.f), 255.f);
+						for (int r1 = -span; r1 <= span; r1++) {
+							inp[2][1] = fmin_ref(fmax_ref(inp0[2][1] + (float) r1 * grid_step(2), 0.f), 255.f);
+							expand_endpoints(eq, wk, inp);
+							build_ramp(rmp[2], wk[2], np);
+							float mse = 0.f;
+							const int len = eq ? 1 : np;
+							for (int k = 0; k < n; k++) {
+								float me = 10000000.f;
+								for (int r = 0; r < len; r++) {
+									const float d = rmp[2][r] - blk[k][2];
+									me = fmin_ref(me, err_gb[r][k] + d * d * chan_weight(2));
+								}
+								mse += me * rpt[k];
+							}
+							if (mse < best) {
+								best = mse;
+								for (int k = 0; k < 2; k++)
+									for (int j = 0; j < 3; j++) out[j][k] = inp[j][k];
+							}
+						}
+					}
+				}
+			}
+		}
+	}
 	return best;
 }
 
@@ -329,7 +410,9 @@ B1_HDN void fit_endpoints(float result[3][2], const float in255[16][3], const fl
 			}
 			grid[j][k] = floorf(r / grid_step(j)) * grid_step(j);
 		}
-	refine(result, grid, in255, rpt, n, np, steps);
+	// `steps` carries the b3DRefinement option in bit 8 (kRefine3D)
+	if (steps & kRefine3D) refine3d(result, grid, in255, rpt, n, np, steps & 0xff);
+	else refine(result, grid, in255, rpt, n, np, steps);
 }
 
 // CompRGBABlock (:1209-1297). in = 16 RGBA texels 0..1. Returns the clustering error; ep[channel B,G,R][2], idx[16].

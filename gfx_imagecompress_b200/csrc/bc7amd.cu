@@ -499,7 +499,10 @@ struct __align__(16) CubeScratch {
 	Task task[kMaxTasks];
 	uint64_t tab[4 * 12];     // ramp tables of the running item: [lattice][channel * 4 + endpoint combination]
 	uint32_t item_ep[32][6];  // expanded endpoint candidates of the batch's items (cube_item_setup_u8)
+	uint32_t lbs[4 * 12];     // second pass: per-ramp bounds of the running item (cube_bound_u8)
+	uint32_t plane[12];       //              channel planes of the running task
 	uint32_t px[16];
+	uint8_t surv[256];        //              corner ids of the running item whose bound can still beat the first pass
 	uint8_t item_ti[32], item_qp[32];
 	uint8_t order[kMaxTasks];
 };
@@ -544,8 +547,59 @@ __device__ __forceinline__ void cube_item_corners(const CubeScratch &ws, const u
 	}
 }
 
+// The same for an item of the SECOND pass, where only corners strictly better than the first pass's error matter: the
+// 12 bounds per lattice over the lanes, the corners whose bound does not exceed `thr` compacted into a list (ballot-free:
+// per-lane masks + prefix sum), one surviving corner per lane and round.  thr follows the best error found.
+template <int CLOG>
+__device__ __forceinline__ void cube_item_pruned(CubeScratch &ws, const uint32_t (&d)[16], int n, int nlb, int qp, unsigned lane, uint32_t &thr,
+																								 uint64_t &lane_best, uint32_t *best_pal) {
+	constexpr int C = 1 << CLOG;
+	const int nl = 1 << nlb;
+	for (int b = (int) lane; b < nl * 12; b += 32) ws.lbs[b] = cube_bound_u8<CLOG>(ws.tab[b], ws.plane + 4 * ((b >> 2) % 3), n);
+	__syncwarp();
+	uint32_t mask = 0;
+#pragma unroll
+	for (int r = 0; r < 8; r++)
+		if (r < 2 * nl && cube_cid_bound(ws.lbs, (int) lane + 32 * r) <= thr) mask |= 1u << r;
+	const int mine = __popc(mask);
+	int incl = mine;
+#pragma unroll
+	for (int dlt = 1; dlt < 32; dlt <<= 1) {
+		const int v = __shfl_up_sync(FULL, incl, dlt);
+		if ((int) lane >= dlt) incl += v;
+	}
+	const int S = __shfl_sync(FULL, incl, 31);
+	if (S == 0) return; // (uniform) nothing in this item can beat the first pass
+	int at = incl - mine;
+	while (mask) {
+		const int r = __ffs(mask) - 1;
+		mask &= mask - 1;
+		ws.surv[at++] = (uint8_t) (lane + 32u * r);
+	}
+	__syncwarp();
+	uint32_t item_min = 0xffffffffu;
+#pragma unroll 1
+	for (int s0 = 0; s0 < S; s0 += 32) {
+		if (s0 + (int) lane < S) {
+			const int cid = ws.surv[s0 + lane];
+			uint32_t pal[C];
+			cube_cid_palette<CLOG>(ws.tab, cid, pal);
+			const uint32_t e = cube_corner_error_u8<CLOG>(pal, d, n);
+			const uint32_t key = cube_cid_key(e, cid);
+			const uint64_t k64 = ((uint64_t) (key >> 8) << 16) | ((uint64_t) qp << 8) | (uint64_t) (key & 255u);
+			item_min = umin32(item_min, e);
+			if (k64 < lane_best) {
+				lane_best = k64;
+#pragma unroll
+				for (int c = 0; c < C; c++) best_pal[c] = pal[c];
+			}
+		}
+	}
+	thr = umin32(thr, __reduce_min_sync(FULL, item_min));
+}
+
 // ep_shaker_d for all tasks of the warp. On return task[i].err_o / best_idx hold its result.
-__device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, unsigned lane) {
+__device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, bool prune2, unsigned lane) {
 	if ((int) lane < ntasks) {
 		Task &t = ws.task[lane];
 		t.err_o = A7_HUGE;
@@ -563,6 +617,8 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 		AMD_COUNT(6, total);
 		AMD_COUNT(10, 1);
 		int cur_ti = -1, n = 0, clog = 3, nlb = 0, bcc = 0;
+		uint32_t thr = 0xffffffffu; // second pass: what a corner has to beat (the first pass's error - 1, then the best found)
+		const bool prune = prune2 && pass == 1;
 		uint32_t d[16];
 #pragma unroll
 		for (int i = 0; i < 16; i++) d[i] = 0;
@@ -612,6 +668,17 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 					nlb = t.type == BCC ? 2 : (t.type == SAME_PAR ? 1 : 0);
 					lane_best = ~0ull;
 					cur_ti = ti;
+					if (prune) {
+						__syncwarp();
+						if (lane < 12) {
+							const int k = (int) lane >> 2, w = (int) lane & 3;
+							uint32_t v = 0;
+							for (int b = 0; b < 4; b++)
+								if (4 * w + b < t.n) v |= ((t.d[4 * w + b] >> (8 * k)) & 255u) << (8 * b);
+							ws.plane[lane] = v;
+						}
+						thr = t.err_o >= 1. ? (uint32_t) t.err_o - 1u : 0u;
+					}
 				}
 				// ramp tables of the item's lattices, 4 entries per lane and step
 				{
@@ -625,8 +692,13 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 				}
 				__syncwarp();
 				const int qp = ws.item_qp[j];
-				if (clog == 2) cube_item_corners<2>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
-				else cube_item_corners<3>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
+				if (prune) {
+					if (clog == 2) cube_item_pruned<2>(ws, d, n, nlb, qp, lane, thr, lane_best, best_pal);
+					else cube_item_pruned<3>(ws, d, n, nlb, qp, lane, thr, lane_best, best_pal);
+				} else {
+					if (clog == 2) cube_item_corners<2>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
+					else cube_item_corners<3>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
+				}
 				__syncwarp();
 			}
 		}
@@ -691,7 +763,7 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 			}
 		}
 		__syncwarp();
-		cube_phase(T, ws, lut2, lut3, ntasks, lane);
+		cube_phase(T, ws, lut2, lut3, ntasks, p.mode == 0, lane); // (second-pass pruning pays where an item has 256 corners: mode 0; mode 2 with 64 measured 2x slower)
 		if ((int) lane < ntasks) {
 			p.s.c_idx[(size_t) block * kMaxTasks + lane] = ws.task[lane].best_idx;
 			p.s.c_err[(size_t) block * kMaxTasks + lane] = ws.task[lane].err_o;

@@ -698,6 +698,58 @@ A7_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t acc) {
 	return acc;
 #endif
 }
+// ---- exact pruning of the SECOND pass of ep_shaker_d ----------------------------------------------------------------
+// The second pass of a task only matters where it is STRICTLY better than the first (:1372-1400), so a corner whose lower
+// bound reaches the first pass's error can be skipped.  Bound (cube_search_pruned_u8): the error of a corner is at least the
+// sum over the three channels of sum_i min_c (ramp[c] - d_i,k)^2 -- twelve per-channel sums per lattice (cube_bound_u8)
+// bound all its 64 corners.  A corner is named cid = lattice << 6 | z << 4 | y << 2 | x.
+// plane[k * 4 + w] = channel k of texels 4w .. 4w+3 (pads 0): see window_planes_u8; pl = the four words of one channel
+template <int CLOG> A7_HD uint32_t cube_bound_u8(uint64_t ramp, const uint32_t *pl, int n) {
+	constexpr int C = 1 << CLOG;
+	uint32_t rc[C];
+#pragma unroll
+	for (int c = 0; c < C; c++) rc[c] = byte_of(ramp, c) * 0x01010101u;
+	const int nw = (n + 3) >> 2;
+	const uint32_t last = (n & 3) ? ((1u << (8 * (n & 3))) - 1u) : 0xffffffffu;
+	uint32_t acc = 0;
+#pragma unroll
+	for (int w = 0; w < 4; w++) {
+		if (w >= nw) break;
+		const uint32_t dw = pl[w];
+		uint32_t m = 0xffffffffu;
+#pragma unroll
+		for (int c = 0; c < C; c++) m = vmin4_u8(m, vabsdiff4_u8(rc[c], dw));
+		if (w == nw - 1) m &= last;
+		acc = dot4_u8(m, m, acc);
+	}
+	return acc;
+}
+A7_HD uint32_t cube_cid_bound(const uint32_t *lbs, int cid) {
+	const uint32_t *l = lbs + 12 * (cid >> 6);
+	return l[cid & 3] + l[4 + ((cid >> 2) & 3)] + l[8 + ((cid >> 4) & 3)];
+}
+template <int CLOG> A7_HD void cube_cid_palette(const uint64_t *tab, int cid, uint32_t *pal) {
+	constexpr int C = 1 << CLOG;
+	const uint64_t *tl = tab + 12 * (cid >> 6);
+	const uint64_t tx = tl[cid & 3], ty = tl[4 + ((cid >> 2) & 3)], tz = tl[8 + ((cid >> 4) & 3)];
+#pragma unroll
+	for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<2>(put_ramp_byte<1>(put_ramp_byte<0>(0u, tx, c), ty, c), tz, c);
+}
+A7_HD uint32_t cube_cid_key(uint32_t err, int cid) { return (err << 8) | (uint32_t) (cid & 0xc0) | (uint32_t) gray_position(cid & 63); }
+template <int CLOG> A7_HD uint32_t cube_corner_error_u8(const uint32_t *pal, const uint32_t (&d)[16], int n) {
+	constexpr int C = 1 << CLOG;
+	uint32_t err = 0;
+#pragma unroll
+	for (int t = 0; t < 16; t++) {
+		if (t >= n) break;
+		uint32_t m = sq_dist4(pal[0], d[t]);
+#pragma unroll
+		for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], d[t]));
+		err += m;
+	}
+	return err;
+}
+
 // ---- ramps from a difference table ---------------------------------------------------------------------------------
 // ramp entry c between expanded endpoints e1, e2 = floor((2 D e1 + D + 2 c (e2 - e1)) / (2 D)) = e1 + off(e2 - e1, c), and
 // every entry stays within 0 .. 255, so a whole ramp is a byte-parallel add (e2 >= e1) or subtract of a table word: no

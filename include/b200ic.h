@@ -70,7 +70,7 @@ typedef enum b200ic_format {
 typedef struct b200ic_opts {
 	float bc1_alpha_threshold;   /* 0..1; <=0 disables punch-through. default 128/255 (reference quirk: active by default) */
 	int32_t amd_refinement_steps;/* default 1 */
-	int32_t amd_3d_refinement;   /* default 0 (non-zero unsupported) */
+	int32_t amd_3d_refinement;   /* default 0; non-zero: Refine3D for BC1 / BC2 / BC3 (src/amd_bcx_body.cpp:808-932) */
 	int32_t amd_adaptive_weights;/* default 0 (non-zero unsupported: reads uninitialised memory in the reference) */
 	int32_t amd_mode_mask;       /* default 0xFF (BC7 / BC6H) */
 	int32_t src_has_alpha;       /* BC7: source has 4 channels (filled by the image API) */

@@ -9,18 +9,27 @@ from gfx_imagecompress_b200 import synth
 from oracle.ref import BC1, default_opts
 
 
-@pytest.mark.parametrize("thr,steps", [(128 / 255.0, 1), (0.0, 1), (128 / 255.0, 2)])
-def test_core_hostbuild_matches_reference(ref, thr, steps):
+@pytest.mark.parametrize("thr,steps,r3d", [(128 / 255.0, 1, False), (0.0, 1, False), (128 / 255.0, 2, False), (128 / 255.0, 1, True)])
+def test_core_hostbuild_matches_reference(ref, thr, steps, r3d):
+    """r3d = the b3DRefinement option (Refine3D, src/amd_bcx_body.cpp:808-932): bit 8 of the core's `steps` argument."""
     import hostbuild
     L = hostbuild.load()
     for name, px, fmt in cases.rgba_cases(small=True):
         if px.shape[2] != 4 or px.shape[0] % 4 or px.shape[1] % 4:
             continue
         fb = cases.to_blocks_f32(px)
-        got = hostbuild.bc1_blocks(L, fb, thr, steps)
-        want = np.stack([ref.bc1_block(b, thr, steps) for b in fb])
+        if r3d:
+            fb = fb[:48]  # 729 candidate ramps per fit: keep the CPU suite short
+        got = hostbuild.bc1_blocks(L, fb, thr, steps | (0x100 if r3d else 0))
+        want = np.stack([_ref_block(ref, b, thr, steps, r3d) for b in fb])
         bad = np.flatnonzero((got != want).any(axis=1))
         assert bad.size == 0, f"{name}: {bad.size}/{len(want)} blocks differ, first {bad[:5]}"
+
+
+def _ref_block(ref, b, thr, steps, r3d=False):
+    out = np.zeros(8, np.uint8)
+    ref.lib.Image_CompressAMDBC1Block(np.ascontiguousarray(b, np.float32).ctypes.data, False, r3d, steps, thr, out.ctypes.data)
+    return out
 
 
 @pytest.mark.gpu
@@ -55,8 +64,13 @@ def test_options_and_image_api(engine, ref):
     assert np.array_equal(dst.blocks(8), want)
     d1 = engine.ImageCompress_Compress(1, False, engine.Image(px, fmt))  # Image_CT_DXBC1
     assert np.array_equal(d1.blocks(8), ref.encode(BC1, px, fmt))
-    # unsupported knobs fail loudly (NULL), never a silent fallback
-    assert engine.Image_CompressAMDBC1(engine.Image(px, fmt), amdOptions=(True, False, 1, 0xFF)) is None
+    # b3DRefinement (Refine3D): 729 candidate ramps per fit, still the reference's bytes
+    small = np.ascontiguousarray(px[:64, :64])
+    dst = engine.Image_CompressAMDBC1(engine.Image(small, fmt), amdOptions=(True, False, 1, 0xFF))
+    want = ref.encode(BC1, small, fmt, opts=default_opts(amd_3d_refinement=1))
+    assert dst is not None and np.array_equal(dst.blocks(8), want)
+    # unsupported knobs fail loudly (NULL), never a silent fallback: AdaptiveColourWeights reads uninitialised memory in the reference
+    assert engine.Image_CompressAMDBC1(engine.Image(px, fmt), amdOptions=(False, True, 1, 0xFF)) is None
 
 
 @pytest.mark.gpu

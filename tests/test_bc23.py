@@ -94,7 +94,7 @@ def test_unsupported_block_arguments_fail_loudly(engine, capfd):
     fb = cases.to_blocks_f32(synth.rgba8_gradnoise(8, 8, 1, "opaque"))[0]
     out = engine.Image_CompressAMDMultiModeLDRBlock(fb, quality=0.5)
     assert (out == 0xFF).all()
-    out = engine.Image_CompressAMDBC1Block(fb, refine3d=True)
+    out = engine.Image_CompressAMDBC1Block(fb, adaptive=True)
     assert (out == 0xFF).all()
     err = capfd.readouterr().err
     assert "Image_CompressAMDMultiModeLDRBlock" in err and "Image_CompressAMDBC1Block" in err
