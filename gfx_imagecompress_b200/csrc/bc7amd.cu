@@ -114,6 +114,7 @@ struct AmdParams {
 	int mode;              // phase kernels: the mode of this pass
 	real *best_err;        // per block of the image: error of the block currently in dst (carried from pass to pass)
 	int first;             // first pass of the sequence: nothing to compare with
+	uint32_t *next_block;  // persistent kernels: the launch's work counter (zero at launch), see fetch_block
 	AmdScratch s;
 };
 
@@ -127,6 +128,15 @@ __device__ __forceinline__ void unpack_idx(uint64_t v, int *idx, int n) {
 }
 __device__ __forceinline__ uint32_t pack_ep(const int e[4]) {
 	return (uint32_t) (e[0] & 255) | ((uint32_t) (e[1] & 255) << 8) | ((uint32_t) (e[2] & 255) << 16) | ((uint32_t) (e[3] & 255) << 24);
+}
+
+// The persistent kernels (cube, window) hand out the blocks of the chunk one at a time from a counter: the block times
+// are data dependent (a mode is skipped for half of the benchmark image), so any static split leaves SMs idle at the end
+// of a launch (4 .. 6 % of every launch with 8 CTAs per resident slot).
+__device__ __forceinline__ uint32_t fetch_block(uint32_t *counter, unsigned lane) {
+	uint32_t b = 0;
+	if (lane == 0) b = atomicAdd(counter, 1u);
+	return __shfl_sync(FULL, b, 0);
 }
 
 struct BlockCoord {
@@ -729,10 +739,9 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 	}
 }
 
-// Persistent: the grid is sized to the SMs, every warp strides over the blocks of the chunk; the two difference tables
-// of the ramps (6 KB, bc7amd_int.cuh) are built once per CTA.
+// Persistent: one CTA per resident slot, every warp takes the next block of the chunk from the launch's counter; the two
+// difference tables of the ramps (6 KB, bc7amd_int.cuh) are built once per CTA.
 constexpr int kCubeCtasPerSm = 5;
-constexpr int kWaves = 8; // CTAs per resident slot: the hardware scheduler evens out the data-dependent block times, the tables amortise over ~100 blocks
 __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(const AmdParams p) {
 	__shared__ CubeScratch scratch[kWarps];
 	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
@@ -746,7 +755,9 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 	const ShakeParams sp = single_index_shake_params(p.mode);
 	const int subsets = mi.subsets, ntasks = mi.alpha == 2 ? dual_shape(mi).ntasks : 8 * subsets;
 #pragma unroll 1
-	for (uint32_t block = blockIdx.x * kWarps + warp; block < p.n_blocks; block += gridDim.x * kWarps) {
+	for (;;) {
+		const uint32_t block = fetch_block(p.next_block, lane);
+		if (block >= p.n_blocks) break;
 		if (p.s.q_top[(size_t) block * 8] == 0xffu) continue; // whole warp: mode not searched for this block
 		const BlockCoord bc = block_coord(p, block);
 		__syncwarp();
@@ -1128,8 +1139,11 @@ __global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_windo
 	WindowScratch &ws = scratch[warp];
 	const Tables T{p.sp};
 #pragma unroll 1
-	for (uint32_t block = blockIdx.x * kWindowWarps + warp; block < p.n_blocks; block += gridDim.x * kWindowWarps)
+	for (;;) {
+		const uint32_t block = fetch_block(p.next_block, lane);
+		if (block >= p.n_blocks) break;
 		window_block(p, ws, T, lut2, lut3, block, lane);
+	}
 }
 
 // =====================================================================================================================
@@ -1507,6 +1521,7 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	p.sp = g_sp_table_host[dev];
 	p.mode_mask = (uint32_t) opts.amd_mode_mask & 0xffu;
 	p.mode = 0;
+	p.next_block = nullptr;
 	p.s = AmdScratch{nullptr, nullptr, nullptr, nullptr};
 	// 8-bit sources: every component is an exact integer, the exact INT32 shakers apply (bc7amd_int.cuh)
 	const bool u8 = img.format == B200IC_FMT_R8 || img.format == B200IC_FMT_RG8 || img.format == B200IC_FMT_RGB8 ||
@@ -1515,15 +1530,16 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	const uint32_t chunk = (uint32_t) (total_blocks < kChunkBlocks ? total_blocks : kChunkBlocks);
 	unsigned char *scratch = nullptr;
 	const size_t per_block = sizeof(uint64_t) * kMaxTasks * 2 + sizeof(real) * kMaxTasks + 8;
+	constexpr size_t kCounterBytes = 256; // work counters of the persistent launches of one chunk (<= 15 launches)
 	e = cudaMallocAsync((void **) &p.best_err, total_blocks * sizeof(real), stream);
 	if (e != cudaSuccess) return e;
 	if (u8) {
-		e = cudaMallocAsync((void **) &scratch, (size_t) chunk * per_block, stream);
+		e = cudaMallocAsync((void **) &scratch, kCounterBytes + (size_t) chunk * per_block, stream);
 		if (e != cudaSuccess) {
 			cudaFreeAsync(p.best_err, stream);
 			return e;
 		}
-		p.s.q_idx = reinterpret_cast<uint64_t *>(scratch);
+		p.s.q_idx = reinterpret_cast<uint64_t *>(scratch + kCounterBytes);
 		p.s.c_idx = p.s.q_idx + (size_t) chunk * kMaxTasks;
 		p.s.c_err = reinterpret_cast<real *>(p.s.c_idx + (size_t) chunk * kMaxTasks);
 		p.s.q_top = reinterpret_cast<uint8_t *>(p.s.c_err + (size_t) chunk * kMaxTasks);
@@ -1535,9 +1551,14 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 		p.n_blocks = (uint32_t) (total_blocks - b0 < chunk ? total_blocks - b0 : chunk);
 		const unsigned warp_grid = (p.n_blocks + kWarps - 1) / kWarps;
 		const unsigned window_ctas = (p.n_blocks + kWindowWarps - 1) / kWindowWarps;
-		const unsigned window_grid = window_ctas < (unsigned) (sms * kWindowCtasPerSm * kWaves) ? window_ctas : (unsigned) (sms * kWindowCtasPerSm * kWaves);
-		const unsigned cube_grid = warp_grid < (unsigned) (sms * kCubeCtasPerSm * kWaves) ? warp_grid : (unsigned) (sms * kCubeCtasPerSm * kWaves);
+		const unsigned window_grid = window_ctas < (unsigned) (sms * kWindowCtasPerSm) ? window_ctas : (unsigned) (sms * kWindowCtasPerSm);
+		const unsigned cube_grid = warp_grid < (unsigned) (sms * kCubeCtasPerSm) ? warp_grid : (unsigned) (sms * kCubeCtasPerSm);
 		int passes = 0;
+		uint32_t *counter = reinterpret_cast<uint32_t *>(scratch);
+		if (u8) {
+			e = cudaMemsetAsync(scratch, 0, kCounterBytes, stream);
+			if (e != cudaSuccess) break;
+		}
 		for (int vi = 0; vi < 8; vi++) {
 			const int mode = mode_visit_order(vi);
 			if (!u8) { // one fused launch: the generic kernel walks the modes itself
@@ -1569,10 +1590,12 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 				}
 				if (mode != 7) {
 					ProfScope ps(stream, mode, 1);
+					p.next_block = counter++;
 					amd_cube_kernel<<<cube_grid, kWarps * 32, 0, stream>>>(p);
 				}
 				{
 					ProfScope ps(stream, mode, 2);
+					p.next_block = counter++;
 					amd_window_kernel<<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch), stream>>>(p);
 				}
 				launches += mode != 7 ? 3 : 2;
@@ -1581,7 +1604,7 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 		}
 	}
 	count_launches(launches - 1);
-	e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaGetLastError();
 	if (scratch) cudaFreeAsync(scratch, stream);
 	cudaFreeAsync(p.best_err, stream);
 	return e;

@@ -690,6 +690,16 @@ A7_HD uint32_t vmin4_u8(uint32_t a, uint32_t b) {
 	return r;
 #endif
 }
+A7_HD uint32_t perm_bytes(uint32_t lo, uint32_t hi, uint32_t sel) { // byte b of the result = byte (sel >> 4b & 7) of hi:lo
+#if defined(__CUDA_ARCH__)
+	return __byte_perm(lo, hi, sel);
+#else
+	const uint64_t v = (uint64_t) lo | ((uint64_t) hi << 32);
+	uint32_t r = 0;
+	for (int b = 0; b < 4; b++) r |= (uint32_t) ((v >> (8 * ((sel >> (4 * b)) & 7u))) & 255u) << (8 * b);
+	return r;
+#endif
+}
 A7_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t acc) {
 #if defined(__CUDA_ARCH__)
 	return __dp4a(a, b, acc);
@@ -704,6 +714,23 @@ A7_HD uint32_t dot4_u8(uint32_t a, uint32_t b, uint32_t acc) {
 // sum over the three channels of sum_i min_c (ramp[c] - d_i,k)^2 -- twelve per-channel sums per lattice (cube_bound_u8)
 // bound all its 64 corners.  A corner is named cid = lattice << 6 | z << 4 | y << 2 | x.
 // plane[k * 4 + w] = channel k of texels 4w .. 4w+3 (pads 0): see window_planes_u8; pl = the four words of one channel
+// (sm_100a has no byte-wise minimum -- __vminu4 is a dozen instructions -- but a native 16x2 one: the four absolute
+// differences of a word are spread over two half-word pairs by byte permutes and reduced with VIMNMX3.U16x2)
+A7_HD uint32_t vmin3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+	return __vimin3_u16x2(a, b, c);
+#else
+	uint32_t r = 0;
+	for (int k = 0; k < 2; k++) {
+		uint32_t x = (a >> (16 * k)) & 0xffffu;
+		const uint32_t y = (b >> (16 * k)) & 0xffffu, z = (c >> (16 * k)) & 0xffffu;
+		x = x < y ? x : y;
+		x = x < z ? x : z;
+		r |= x << (16 * k);
+	}
+	return r;
+#endif
+}
 template <int CLOG> A7_HD uint32_t cube_bound_u8(uint64_t ramp, const uint32_t *pl, int n) {
 	constexpr int C = 1 << CLOG;
 	uint32_t rc[C];
@@ -716,9 +743,14 @@ template <int CLOG> A7_HD uint32_t cube_bound_u8(uint64_t ramp, const uint32_t *
 	for (int w = 0; w < 4; w++) {
 		if (w >= nw) break;
 		const uint32_t dw = pl[w];
-		uint32_t m = 0xffffffffu;
+		uint32_t mlo = 0xffffffffu, mhi = 0xffffffffu; // running minima of texels (0, 1) / (2, 3) of the word, one per half-word
 #pragma unroll
-		for (int c = 0; c < C; c++) m = vmin4_u8(m, vabsdiff4_u8(rc[c], dw));
+		for (int c = 0; c < C; c += 2) {
+			const uint32_t a0 = vabsdiff4_u8(rc[c], dw), a1 = vabsdiff4_u8(rc[c + 1], dw);
+			mlo = vmin3_u16x2(mlo, perm_bytes(a0, 0u, 0x4140u), perm_bytes(a1, 0u, 0x4140u));
+			mhi = vmin3_u16x2(mhi, perm_bytes(a0, 0u, 0x4342u), perm_bytes(a1, 0u, 0x4342u));
+		}
+		uint32_t m = perm_bytes(mlo, mhi, 0x6420u);
 		if (w == nw - 1) m &= last;
 		acc = dot4_u8(m, m, acc);
 	}
@@ -986,16 +1018,6 @@ A7_HD int endpoint_floor_int(real v, int bits, int use_par, int odd) { // ep_fin
 		else i2 = j;
 	}
 	return (i1 << use_par) + odd;
-}
-A7_HD uint32_t perm_bytes(uint32_t lo, uint32_t hi, uint32_t sel) { // byte b of the result = byte (sel >> 4b & 7) of hi:lo
-#if defined(__CUDA_ARCH__)
-	return __byte_perm(lo, hi, sel);
-#else
-	const uint64_t v = (uint64_t) lo | ((uint64_t) hi << 32);
-	uint32_t r = 0;
-	for (int b = 0; b < 4; b++) r |= (uint32_t) ((v >> (8 * ((sel >> (4 * b)) & 7u))) & 255u) << (8 * b);
-	return r;
-#endif
 }
 // plane[j * 4 + w] = channel j of texels 4w .. 4w+3 (pads 0), all four channels
 A7_HD void window_planes_u8(const uint32_t *d, int n, uint32_t plane[16]) {

@@ -139,7 +139,33 @@ template <int CLOG> static int hb_cube_lane_trial(uint64_t &rng, int bits, int t
 	uint32_t pal[C];
 	cube_lane_palette<CLOG>(tab, nlb, best_lane, best_xy, pal);
 	const uint64_t got_idx = palette_indices_u8<CLOG>(d, n, pal);
-	return (bad_tab || best != want_key || got_idx != want_idx) ? 1 : 0;
+	// the per-channel bounds of the second-pass pruning: equal to the plain definition, and never above a corner's error
+	uint32_t plane[16], lbs[48];
+	window_planes_u8(d, n, plane);
+	int bad_bound = 0;
+	for (int b = 0; b < nl * 12; b++) {
+		const int k = (b >> 2) % 3;
+		lbs[b] = cube_bound_u8<CLOG>(tab[b], plane + 4 * k, n);
+		uint32_t sum = 0;
+		for (int i = 0; i < n; i++) {
+			int m = 255;
+			for (int c = 0; c < C; c++) {
+				int a = (int) ((tab[b] >> (8 * c)) & 255u) - (int) ((d[i] >> (8 * k)) & 255u);
+				a = a < 0 ? -a : a;
+				m = a < m ? a : m;
+			}
+			sum += (uint32_t) (m * m);
+		}
+		if (sum != lbs[b]) bad_bound = 1;
+	}
+	for (int cid = 0; cid < nl * 64; cid++) {
+		uint32_t cp[C];
+		cube_cid_palette<CLOG>(tab, cid, cp);
+		const uint32_t e = cube_corner_error_u8<CLOG>(cp, d, n);
+		if (cube_cid_bound(lbs, cid) > e) bad_bound = 1;
+		if (cube_cid_key(e, cid) < best) bad_bound = 1; // (the lane walk's minimum is the minimum over the corner ids too)
+	}
+	return (bad_tab || bad_bound || best != want_key || got_idx != want_idx) ? 1 : 0;
 }
 // window_item_lut_u8 (table ramps, per-texel sums) against window_item_u8 (cluster sums) on random items
 template <int CLOG> static int hb_window_trial(uint64_t &rng, int size, int bits_total, int dim) {
