@@ -254,6 +254,17 @@ __device__ __forceinline__ void build_dual_index_task(Task &t, const uint32_t *p
 	t.item_base = t.item_count = 0;
 }
 
+// Tasks with the same texel set.  The 3-subset partition tables repeat subsets (36 distinct masks among the 48 of mode 0, 140
+// among the 192 of mode 2), and the 8 partitions the quantiser ranks best are similar: 11 .. 12 % of the 24 tasks of a block
+// repeat an earlier one on the benchmark image.  Quantiser and shakers are pure functions of the texel list and the mode, so
+// the repeat takes the first task's result.  Returns the first task with this lane's texel mask (== lane: not a repeat).
+__device__ __forceinline__ int first_task_with_mask(int subsets, int part, int s, int ntasks, unsigned lane) {
+	uint32_t mask = 0;
+	for (int i = 0; i < 16; i++) mask |= (subset_of(subsets, part, i) == s ? 1u : 0u) << i;
+	const uint32_t key = (int) lane < ntasks ? mask : 0x10000u + lane; // (idle lanes match nobody)
+	return __ffs(__match_any_sync(FULL, key)) - 1;
+}
+
 // Start (or restart) a pass of ep_shaker_d for one task: collapse the indices, handle the single-index case.
 __device__ __noinline__ void cube_begin_pass(const Tables &T, Task &t, uint64_t from) {
 	int index[kMaxEntries];
@@ -515,6 +526,7 @@ struct __align__(16) CubeScratch {
 	uint8_t surv[256];        //              corner ids of the running item whose bound can still beat the first pass
 	uint8_t item_ti[32], item_qp[32];
 	uint8_t order[kMaxTasks];
+	uint8_t same_as[kMaxTasks]; // first task with the same texels (first_task_with_mask)
 };
 
 // Index vector of the pass winner: the palette travels from the winning lane by shuffles, texel i is classified by lane i.
@@ -615,7 +627,12 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 		t.err_o = A7_HUGE;
 		t.best_idx = t.idx_q;
 		t.done = 0;
-		cube_begin_pass(T, t, t.idx_q);
+		if (ws.same_as[lane] == lane) {
+			cube_begin_pass(T, t, t.idx_q);
+		} else { // a repeat: takes the first task's result afterwards
+			t.done = 1;
+			t.item_count = 0;
+		}
 	}
 	__syncwarp();
 #pragma unroll 1
@@ -773,11 +790,20 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 				build_single_index_task(ws.task[lane], ws.px, subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, idx_q);
 			}
 		}
+		{
+			int first = (int) lane;
+			if (subsets == 3) { // (uniform; the 2-subset tables and the dual-index tasks have no repeats)
+				const int a = (int) lane < ntasks ? (int) lane / subsets : 0, s = (int) lane - a * subsets;
+				first = first_task_with_mask(subsets, p.s.q_top[(size_t) block * 8 + a], s, ntasks, lane);
+			}
+			if ((int) lane < ntasks) ws.same_as[lane] = (uint8_t) first;
+		}
 		__syncwarp();
 		cube_phase(T, ws, lut2, lut3, ntasks, p.mode == 0, lane); // (second-pass pruning pays where an item has 256 corners: mode 0; mode 2 with 64 measured 2x slower)
 		if ((int) lane < ntasks) {
-			p.s.c_idx[(size_t) block * kMaxTasks + lane] = ws.task[lane].best_idx;
-			p.s.c_err[(size_t) block * kMaxTasks + lane] = ws.task[lane].err_o;
+			const Task &t = ws.task[ws.same_as[lane]];
+			p.s.c_idx[(size_t) block * kMaxTasks + lane] = t.best_idx;
+			p.s.c_err[(size_t) block * kMaxTasks + lane] = t.err_o;
 		}
 		AMD_T(2);
 	}
@@ -798,6 +824,7 @@ struct __align__(16) WindowScratch {
 	uint32_t px[16];
 	uint8_t item_ti[kWinBatch], item_qp[kWinBatch];
 	uint8_t order[kMaxTasks];
+	uint8_t same_as[kMaxTasks]; // first task with the same texels (first_task_with_mask)
 	uint8_t top[8];
 };
 
@@ -1034,6 +1061,17 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 		if (dual) t.w_index = t.best_idx; // ep_shaker_2_d runs on ep_shaker_d's indices only (src/amd_bc7_body.cpp:1120-1160)
 		window_planes_u8(t.d, t.n, t.plane);
 	}
+	{
+		int first = (int) lane;
+		if (subsets == 3) { // (uniform) repeats of a texel set take the first task's result
+			const int a = (int) lane < ntasks ? (int) lane / subsets : 0, s = (int) lane - a * subsets;
+			first = first_task_with_mask(subsets, ws.top[a], s, ntasks, lane);
+		}
+		if ((int) lane < ntasks) {
+			ws.same_as[lane] = (uint8_t) first;
+			if (first != (int) lane) ws.task[lane].w_active = 0;
+		}
+	}
 	__syncwarp();
 	if (dual) {
 		window_phase(T, ws, lut2, lut3, ntasks, lane);
@@ -1084,7 +1122,7 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 	if (cube) {
 		if ((int) lane < ntasks) {
 			Task &t = ws.task[lane];
-			t.w_active = (t.err_o < t.w_err_o) ? 1 : 0;
+			t.w_active = (ws.same_as[lane] == lane && t.err_o < t.w_err_o) ? 1 : 0;
 			t.w_index = t.best_idx;
 		}
 		__syncwarp();
@@ -1092,7 +1130,7 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 		AMD_T(4);
 	}
 	if ((int) lane < ntasks) {
-		const Task &t = ws.task[lane];
+		const Task &t = ws.task[ws.same_as[lane]];
 		ShakeOut o;
 		o.err = t.w_err_o;
 		o.idx = t.w_best_idx;
