@@ -25,6 +25,7 @@
 #include "kernels.h"
 #include "bc7amd_block.cuh"
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 namespace b200ic {
@@ -34,7 +35,8 @@ namespace {
 using namespace amd7;
 
 constexpr int kWarps = 4;
-constexpr int kMaxTasks = 24;   // single-index: 8 attempts x 3 subsets; dual-index: 8 combos x 2
+constexpr int kMaxTasks = 24;   // tasks per block -- single-index: 8 attempts x 3 subsets; dual-index: 8 combos x 2
+constexpr int kWarpTasks = 32;  // tasks per warp: a warp of the cube / window kernels takes 2 (mode 4) or 4 (mode 5) blocks at a time
 constexpr uint32_t kChunkBlocks = 1u << 19; // blocks per pass over the phase kernels (bounds the scratch: 584 B per block)
 
 uint32_t *g_sp_table_host[16] = {};
@@ -517,16 +519,16 @@ __global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_dual_kernel(const Am
 // cube kernel (ep_shaker_d)
 // =====================================================================================================================
 struct __align__(16) CubeScratch {
-	Task task[kMaxTasks];
+	Task task[kWarpTasks];
 	uint64_t tab[4 * 12];     // ramp tables of the running item: [lattice][channel * 4 + endpoint combination]
 	uint32_t item_ep[32][6];  // expanded endpoint candidates of the batch's items (cube_item_setup_u8)
 	uint32_t lbs[4 * 12];     // second pass: per-ramp bounds of the running item (cube_bound_u8)
 	uint32_t plane[12];       //              channel planes of the running task
-	uint32_t px[16];
+	uint32_t px[4][16];       // texels of the warp's blocks
 	uint8_t surv[256];        //              corner ids of the running item whose bound can still beat the first pass
 	uint8_t item_ti[32], item_qp[32];
-	uint8_t order[kMaxTasks];
-	uint8_t same_as[kMaxTasks]; // first task with the same texels (first_task_with_mask)
+	uint8_t order[kWarpTasks];
+	uint8_t same_as[kWarpTasks]; // first task with the same texels (first_task_with_mask); 0xff: no work (block absent / mode skipped)
 };
 
 // Index vector of the pass winner: the palette travels from the winning lane by shuffles, texel i is classified by lane i.
@@ -771,39 +773,45 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 	const ModeInfo mi = mode_info(p.mode);
 	const ShakeParams sp = single_index_shake_params(p.mode);
 	const int subsets = mi.subsets, ntasks = mi.alpha == 2 ? dual_shape(mi).ntasks : 8 * subsets;
+	// dual-index modes: 16 / 8 tasks per block -- the warp takes 2 / 4 blocks at a time so that the lane = task and
+	// lane = item stages run on full warps
+	const int bpw = mi.alpha == 2 ? 32 / ntasks : 1, wtasks = bpw * ntasks;
+	const int sub = (int) lane / ntasks, tk = (int) lane - sub * ntasks; // this lane's task: block of the group, task of the block
 #pragma unroll 1
 	for (;;) {
-		const uint32_t block = fetch_block(p.next_block, lane);
-		if (block >= p.n_blocks) break;
-		if (p.s.q_top[(size_t) block * 8] == 0xffu) continue; // whole warp: mode not searched for this block
-		const BlockCoord bc = block_coord(p, block);
+		const uint32_t block0 = fetch_block(p.next_block, lane) * (uint32_t) bpw;
+		if (block0 >= p.n_blocks) break;
+		const uint32_t block = block0 + (uint32_t) sub;
+		const bool have = sub < bpw && block < p.n_blocks && p.s.q_top[(size_t) block * 8] != 0xffu; // (0xff: mode not searched for this block)
+		if (!__any_sync(FULL, have)) continue;
 		__syncwarp();
-		if (lane < 16) ws.px[lane] = fetch_rgba_u8(p.img, bc, (int) lane);
+		for (int b = (int) lane >> 4; b < bpw; b += 2) // 16 lanes per block
+			if (block0 + b < p.n_blocks) ws.px[b][lane & 15] = fetch_rgba_u8(p.img, block_coord(p, block0 + b), (int) lane & 15);
 		__syncwarp();
 		AMD_T0();
-		if ((int) lane < ntasks) {
-			const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + lane];
+		if (have) {
+			const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + tk];
 			if (mi.alpha == 2) {
-				build_dual_index_task(ws.task[lane], ws.px, mi, (int) lane, idx_q);
+				build_dual_index_task(ws.task[lane], ws.px[sub], mi, tk, idx_q);
 			} else {
-				const int a = (int) lane / subsets, s = (int) lane - a * subsets;
-				build_single_index_task(ws.task[lane], ws.px, subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, idx_q);
+				const int a = tk / subsets, s = tk - a * subsets;
+				build_single_index_task(ws.task[lane], ws.px[0], subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, idx_q);
 			}
 		}
 		{
-			int first = (int) lane;
+			int first = have ? (int) lane : 0xff;
 			if (subsets == 3) { // (uniform; the 2-subset tables and the dual-index tasks have no repeats)
 				const int a = (int) lane < ntasks ? (int) lane / subsets : 0, s = (int) lane - a * subsets;
-				first = first_task_with_mask(subsets, p.s.q_top[(size_t) block * 8 + a], s, ntasks, lane);
+				first = first_task_with_mask(subsets, p.s.q_top[(size_t) block0 * 8 + a], s, ntasks, lane);
 			}
-			if ((int) lane < ntasks) ws.same_as[lane] = (uint8_t) first;
+			if ((int) lane < wtasks) ws.same_as[lane] = (uint8_t) first;
 		}
 		__syncwarp();
-		cube_phase(T, ws, lut2, lut3, ntasks, p.mode == 0, lane); // (second-pass pruning pays where an item has 256 corners: mode 0; mode 2 with 64 measured 2x slower)
-		if ((int) lane < ntasks) {
+		cube_phase(T, ws, lut2, lut3, wtasks, p.mode == 0, lane); // (second-pass pruning pays where an item has 256 corners: mode 0; mode 2 with 64 measured 2x slower)
+		if (have) {
 			const Task &t = ws.task[ws.same_as[lane]];
-			p.s.c_idx[(size_t) block * kMaxTasks + lane] = t.best_idx;
-			p.s.c_err[(size_t) block * kMaxTasks + lane] = t.err_o;
+			p.s.c_idx[(size_t) block * kMaxTasks + tk] = t.best_idx;
+			p.s.c_err[(size_t) block * kMaxTasks + tk] = t.err_o;
 		}
 		AMD_T(2);
 	}
@@ -813,20 +821,25 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 // window kernel (ep_shaker_2_d, best attempt, packing)
 // =====================================================================================================================
 constexpr int kWinBatch = 32; // work items per batch of the window phase
-struct __align__(16) WindowScratch {
-	Task task[kMaxTasks];
+// NT tasks per warp; RS = stride of a channel's results in wres (4: one slot per parity combination; 1: the dual-index
+// modes, whose lattices have no parity)
+template <int NT, int RS> struct __align__(16) WindowScratchT {
+	static constexpr int kResStride = RS;
+	Task task[NT];
 	uint64_t item_key[kWinBatch];
 	uint64_t item_idx[kWinBatch];
-	uint64_t wres[kWinBatch][16]; // window_sub_search_u8 results of the batch: [item][channel * 4 + pp0 * 2 + pp1]
-	real wepa[kWinBatch][8];      // window_item_fit_u8: least-squares endpoints [endpoint * 4 + channel]
-	uint32_t wsel[kWinBatch][4];  //                     byte-permute selectors
-	ShakeOut so[kMaxTasks];
-	uint32_t px[16];
+	uint64_t wres[kWinBatch][4 * RS]; // window_sub_search_u8 results of the batch: [item][channel * RS + pp0 * 2 + pp1]
+	real wepa[kWinBatch][8];          // window_item_fit_u8: least-squares endpoints [endpoint * 4 + channel]
+	uint32_t wsel[kWinBatch][4];      //                     byte-permute selectors
+	ShakeOut so[NT];
+	uint32_t px[NT == kWarpTasks ? 4 : 1][16]; // texels of the warp's blocks
 	uint8_t item_ti[kWinBatch], item_qp[kWinBatch];
-	uint8_t order[kMaxTasks];
-	uint8_t same_as[kMaxTasks]; // first task with the same texels (first_task_with_mask)
+	uint8_t order[NT];
+	uint8_t same_as[NT]; // first task with the same texels (first_task_with_mask)
 	uint8_t top[8];
 };
+using WindowScratch = WindowScratchT<kMaxTasks, 4>;      // single-index modes: one block per warp
+using WindowScratchDual = WindowScratchT<kWarpTasks, 1>; // dual-index modes: 2 (mode 4) / 4 (mode 5) blocks per warp
 
 // Start a round of ep_shaker_2_d for one task (:785-827): collapse, single-index case.
 __device__ __noinline__ void window_begin_round(const Tables &T, Task &t) {
@@ -856,7 +869,8 @@ __device__ __noinline__ void window_begin_round(const Tables &T, Task &t) {
 }
 
 // ep_shaker_2_d for the tasks with w_active set, starting from task.w_index. Results in w_err_o / w_best_idx / w_best_ep.
-__device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, unsigned lane) {
+template <typename WS>
+__device__ __noinline__ void window_phase(const Tables &T, WS &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, int dim, int type, unsigned lane) {
 	if ((int) lane < ntasks) {
 		Task &t = ws.task[lane];
 		t.done = t.w_active ? 0 : 1;
@@ -882,7 +896,7 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, co
 		AMD_COUNT(9, (total + 31) / 32);
 		// every task of a launch has the same dimension and parity type (the endpoint bits differ between the vector and
 		// scalar tasks of the dual-index modes): dim x (1 | 2 | 4) independent searches per item
-		const int dim = ws.task[0].dim, type = ws.task[0].w_bits_total % (2 * dim), use_par = type != 0;
+		const int use_par = type != 0;
 		const int ncombo = type == BCC ? 4 : (type == SAME_PAR ? 2 : 1), per = dim * ncombo;
 		const int nbatch = (total + kWinBatch - 1) / kWinBatch, batch = (total + nbatch - 1) / nbatch; // (even batches)
 		for (int b0 = 0; b0 < total; b0 += batch) {
@@ -914,13 +928,13 @@ __device__ __noinline__ void window_phase(const Tables &T, WindowScratch &ws, co
 				const uint4 pv = *reinterpret_cast<const uint4 *>(t.plane + 4 * j);
 				const uint32_t sel[4] = {sv.x, sv.y, sv.z, sv.w}, plw[4] = {pv.x, pv.y, pv.z, pv.w};
 				const real ep0 = ws.wepa[item][j], ep1 = ws.wepa[item][4 + j];
-				ws.wres[item][j * 4 + pp0 * 2 + pp1] = t.clog == 2 ? window_sub_search_u8<2>(lut2, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1)
+				ws.wres[item][j * WS::kResStride + pp0 * 2 + pp1] = t.clog == 2 ? window_sub_search_u8<2>(lut2, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1)
 																													 : window_sub_search_u8<3>(lut3, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1);
 			}
 			__syncwarp();
 			if ((int) lane < cnt) { // combine
 				uint64_t epo;
-				const uint32_t err = window_item_combine(ws.wres[lane], type, dim, epo);
+				const uint32_t err = window_item_combine(ws.wres[lane], type, dim, epo, WS::kResStride);
 				ws.item_key[lane] = ((uint64_t) err << 8) | (uint64_t) (255 - ws.item_qp[lane]); // `<=`: the LAST minimum wins
 				ws.item_idx[lane] = epo;
 			}
@@ -1026,7 +1040,84 @@ __device__ __forceinline__ void pack_single_index_warp(int mode, int partition, 
 	out1 = (uint64_t) w2 | ((uint64_t) w3 << 32);
 }
 
-// One block of the window kernel
+// A group of 2 / 4 blocks of a dual-index mode (4 / 5): lane = (block of the group, task of the block)
+__device__ __forceinline__ void window_group_dual(const AmdParams &p, WindowScratchDual &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3,
+																									uint32_t group, unsigned lane) {
+	const int mode = p.mode;
+	const ModeInfo mi = mode_info(mode);
+	const DualShape ds = dual_shape(mi);
+	const int ntasks = ds.ntasks, bpw = 32 / ntasks;
+	const int sub = (int) lane / ntasks, tk = (int) lane - sub * ntasks;
+	const uint32_t block0 = group * (uint32_t) bpw, block = block0 + (uint32_t) sub;
+	const bool present = block < p.n_blocks;
+	const bool have = present && p.s.q_top[(size_t) block * 8] != 0xffu; // (0xff: mode not searched for this block)
+	if (p.first && present && !have && tk == 0) {
+		p.dst[p.block0 + block] = make_uint4(0, 0, 0, 0);
+		p.best_err[p.block0 + block] = A7_HUGE;
+	}
+	if (!__any_sync(FULL, have)) return;
+	__syncwarp();
+	for (int b = (int) lane >> 4; b < bpw; b += 2) // 16 lanes per block
+		if (block0 + b < p.n_blocks) ws.px[b][lane & 15] = fetch_rgba_u8(p.img, block_coord(p, block0 + b), (int) lane & 15);
+	__syncwarp();
+	AMD_T0();
+	{
+		Task &t = ws.task[lane];
+		if (have) {
+			build_dual_index_task(t, ws.px[sub], mi, tk, p.s.q_idx[(size_t) block * kMaxTasks + tk]);
+			t.best_idx = p.s.c_idx[(size_t) block * kMaxTasks + tk];
+			t.err_o = p.s.c_err[(size_t) block * kMaxTasks + tk];
+			t.w_index = t.best_idx; // ep_shaker_2_d runs on ep_shaker_d's indices only (src/amd_bc7_body.cpp:1120-1160)
+			window_planes_u8(t.d, t.n, t.plane);
+		} else {
+			t.w_active = 0;
+		}
+	}
+	__syncwarp();
+	window_phase(T, ws, lut2, lut3, kWarpTasks, 3, CART, lane);
+	AMD_T(3);
+	{
+		const Task &t = ws.task[lane];
+		ShakeOut o;
+		o.err = t.w_err_o;
+		o.idx = t.w_best_idx;
+		o.ep[0] = (uint32_t) t.w_best_ep;
+		o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
+		ws.so[lane] = o;
+	}
+	__syncwarp();
+	if (have && tk == 0) { // one lane per block: best combination, packing
+		const ShakeOut *so = ws.so + sub * ntasks;
+		real be = A7_HUGE;
+		int bcm = 0;
+		for (int c = 0; c < ds.combos; c++) {
+			real e = 0;
+			e += so[2 * c].err;
+			e += so[2 * c + 1].err / 3.;
+			if (e < be) { be = e; bcm = c; }
+		}
+		const uint64_t gblock = p.block0 + block;
+		const real carried = p.first ? A7_HUGE : p.best_err[gblock];
+		if (p.first || be < carried) {
+			int epp[2][2][4], idxp[2][16];
+			for (int w = 0; w < 2; w++) {
+				const ShakeOut &o = so[2 * bcm + w];
+				for (int k = 0; k < 4; k++) {
+					epp[w][0][k] = (int) ((o.ep[0] >> (8 * k)) & 255u);
+					epp[w][1][k] = (int) ((o.ep[1] >> (8 * k)) & 255u);
+				}
+				for (int i = 0; i < 16; i++) idxp[w][i] = (int) ((o.idx >> (4 * i)) & 15u);
+			}
+			uint64_t blk[2];
+			pack_dual_index(mode, bcm % ds.nsel, bcm / ds.nsel, epp, idxp, blk);
+			p.dst[gblock] = make_uint4((uint32_t) blk[0], (uint32_t) (blk[0] >> 32), (uint32_t) blk[1], (uint32_t) (blk[1] >> 32));
+			p.best_err[gblock] = be;
+		}
+	}
+	AMD_T(5);
+}
+
+// One block of a single-index mode (0 .. 3, 7)
 __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3,
 																						 uint32_t block, unsigned lane) {
 	const BlockCoord bc = block_coord(p, block);
@@ -1038,27 +1129,25 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 		return;
 	}
 	__syncwarp();
-	if (lane < 16) ws.px[lane] = fetch_rgba_u8(p.img, bc, (int) lane);
+	if (lane < 16) ws.px[0][lane] = fetch_rgba_u8(p.img, bc, (int) lane);
 	if (lane < 8) ws.top[lane] = p.s.q_top[(size_t) block * 8 + lane];
 	__syncwarp();
 	const int mode = p.mode;
 	const ModeInfo mi = mode_info(mode);
 	const ShakeParams sp = single_index_shake_params(mode);
-	const bool dual = mi.alpha == 2;
-	const int subsets = mi.subsets, ntasks = dual ? dual_shape(mi).ntasks : 8 * subsets;
-	const bool cube = dual || sp.dim == 3;
+	const int subsets = mi.subsets, ntasks = 8 * subsets;
+	const bool cube = sp.dim == 3;
+	const int wtype = sp.bits[3] % (2 * sp.dim);
 	AMD_T0();
 	if ((int) lane < ntasks) {
 		const int a = (int) lane / subsets, s = (int) lane - a * subsets;
 		Task &t = ws.task[lane];
 		const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + lane];
-		if (dual) build_dual_index_task(t, ws.px, mi, (int) lane, idx_q);
-		else build_single_index_task(t, ws.px, subsets, ws.top[a], s, sp, idx_q);
+		build_single_index_task(t, ws.px[0], subsets, ws.top[a], s, sp, idx_q);
 		if (cube) {
 			t.best_idx = p.s.c_idx[(size_t) block * kMaxTasks + lane];
 			t.err_o = p.s.c_err[(size_t) block * kMaxTasks + lane];
 		}
-		if (dual) t.w_index = t.best_idx; // ep_shaker_2_d runs on ep_shaker_d's indices only (src/amd_bc7_body.cpp:1120-1160)
 		window_planes_u8(t.d, t.n, t.plane);
 	}
 	{
@@ -1073,51 +1162,8 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 		}
 	}
 	__syncwarp();
-	if (dual) {
-		window_phase(T, ws, lut2, lut3, ntasks, lane);
-		AMD_T(3);
-		if ((int) lane < ntasks) {
-			const Task &t = ws.task[lane];
-			ShakeOut o;
-			o.err = t.w_err_o;
-			o.idx = t.w_best_idx;
-			o.ep[0] = (uint32_t) t.w_best_ep;
-			o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
-			ws.so[lane] = o;
-		}
-		__syncwarp();
-		if (lane == 0) {
-			const DualShape ds = dual_shape(mi);
-			real be = A7_HUGE;
-			int bcm = 0;
-			for (int c = 0; c < ds.combos; c++) {
-				real e = 0;
-				e += ws.so[2 * c].err;
-				e += ws.so[2 * c + 1].err / 3.;
-				if (e < be) { be = e; bcm = c; }
-			}
-			const real carried = p.first ? A7_HUGE : p.best_err[bc.gblock];
-			if (p.first || be < carried) {
-				int epp[2][2][4], idxp[2][16];
-				for (int w = 0; w < 2; w++) {
-					const ShakeOut &o = ws.so[2 * bcm + w];
-					for (int k = 0; k < 4; k++) {
-						epp[w][0][k] = (int) ((o.ep[0] >> (8 * k)) & 255u);
-						epp[w][1][k] = (int) ((o.ep[1] >> (8 * k)) & 255u);
-					}
-					for (int i = 0; i < 16; i++) idxp[w][i] = (int) ((o.idx >> (4 * i)) & 15u);
-				}
-				uint64_t blk[2];
-				pack_dual_index(mode, bcm % ds.nsel, bcm / ds.nsel, epp, idxp, blk);
-				p.dst[bc.gblock] = make_uint4((uint32_t) blk[0], (uint32_t) (blk[0] >> 32), (uint32_t) blk[1], (uint32_t) (blk[1] >> 32));
-				p.best_err[bc.gblock] = be;
-			}
-		}
-		AMD_T(5);
-		return;
-	}
 	// shake_subset (:709-805): ep_shaker_2_d on the quantiser's indices and, where ep_shaker_d won, again on its indices
-	window_phase(T, ws, lut2, lut3, ntasks, lane);
+	window_phase(T, ws, lut2, lut3, ntasks, sp.dim, wtype, lane);
 	AMD_T(3);
 	if (cube) {
 		if ((int) lane < ntasks) {
@@ -1126,7 +1172,7 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 			t.w_index = t.best_idx;
 		}
 		__syncwarp();
-		window_phase(T, ws, lut2, lut3, ntasks, lane);
+		window_phase(T, ws, lut2, lut3, ntasks, sp.dim, wtype, lane);
 		AMD_T(4);
 	}
 	if ((int) lane < ntasks) {
@@ -1166,23 +1212,28 @@ __device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &
 
 // 8 warps per CTA: 2 CTAs (16 warps) fit the 227 KB of shared memory next to one copy of the ramp tables each
 constexpr int kWindowWarps = 8, kWindowCtasPerSm = 2;
-__global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
+template <bool DUAL> __global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
+	using WS = typename std::conditional<DUAL, WindowScratchDual, WindowScratch>::type;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	WindowScratch *scratch = reinterpret_cast<WindowScratch *>(smem_raw);
+	WS *scratch = reinterpret_cast<WS *>(smem_raw);
 	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
 	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWindowWarps * 32);
 	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWindowWarps * 32);
 	__syncthreads();
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-	WindowScratch &ws = scratch[warp];
+	WS &ws = scratch[warp];
 	const Tables T{p.sp};
+	const uint32_t units = DUAL ? (p.n_blocks + (p.mode == 4 ? 1u : 3u)) / (p.mode == 4 ? 2u : 4u) : p.n_blocks; // blocks, or groups of 2 / 4 blocks
 #pragma unroll 1
 	for (;;) {
-		const uint32_t block = fetch_block(p.next_block, lane);
-		if (block >= p.n_blocks) break;
-		window_block(p, ws, T, lut2, lut3, block, lane);
+		const uint32_t unit = fetch_block(p.next_block, lane);
+		if (unit >= units) break;
+		if constexpr (DUAL) window_group_dual(p, ws, T, lut2, lut3, unit, lane);
+		else window_block(p, ws, T, lut2, lut3, unit, lane);
 	}
 }
+// (2 CTAs of 8 warps and their tables fit the shared memory of an SM)
+static_assert(kWindowWarps * sizeof(WindowScratch) + 6144 + 1024 <= 116736 && kWindowWarps * sizeof(WindowScratchDual) + 6144 + 1024 <= 116736, "window scratch: 2 CTAs per SM");
 
 // =====================================================================================================================
 // Modes with few independent tasks per block -- mode 6: ONE partition, ONE subset; modes 4 / 5: 16 / 8 (rotation,
@@ -1536,7 +1587,9 @@ cudaError_t init_bc7amd_tables() {
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(amd_quant_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(DualQuantScratch)));
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch)));
+	e = cudaFuncSetAttribute(amd_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch)));
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(amd_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratchDual)));
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(bc7amd_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(FloatScratch)));
 	if (e != cudaSuccess) return e;
@@ -1634,7 +1687,8 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 				{
 					ProfScope ps(stream, mode, 2);
 					p.next_block = counter++;
-					amd_window_kernel<<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch), stream>>>(p);
+					if (mode == 4 || mode == 5) amd_window_kernel<true><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratchDual), stream>>>(p);
+					else amd_window_kernel<false><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch), stream>>>(p);
 				}
 				launches += mode != 7 ? 3 : 2;
 			}

@@ -1109,7 +1109,7 @@ A7_HD uint64_t window_sub_search_u8(const uint32_t *lut, real ep0, real ep1, con
 	return ((uint64_t) best << 16) | ((uint64_t) (b1 & 255) << 8) | (uint64_t) (b2 & 255);
 }
 // res[j * 4 + pp0 * 2 + pp1] from window_sub_search_u8 (SAME_PAR never reads the mixed-parity entries)
-A7_HD uint32_t window_item_combine(const uint64_t *res, int type, int dim, uint64_t &epo_out) {
+A7_HD uint32_t window_item_combine(const uint64_t *res, int type, int dim, uint64_t &epo_out, int stride = 4) { // res[j * stride + pp0 * 2 + pp1]
 	int64_t err_1 = INT64_MAX;
 	int epo_1[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll 1
@@ -1117,12 +1117,12 @@ A7_HD uint32_t window_item_combine(const uint64_t *res, int type, int dim, uint6
 		const int v0 = type == SAME_PAR ? pn : (pn >> 1), v1 = type == SAME_PAR ? pn : (pn & 1);
 		int64_t e2 = 0;
 #pragma unroll 1
-		for (int j = 0; j < dim; j++) e2 += (int64_t) (res[j * 4 + v0 * 2 + v1] >> 16);
+		for (int j = 0; j < dim; j++) e2 += (int64_t) (res[j * stride + v0 * 2 + v1] >> 16);
 		if (e2 < err_1) {
 			err_1 = e2;
 #pragma unroll 1
 			for (int j = 0; j < dim; j++) {
-				const uint64_t r = res[j * 4 + v0 * 2 + v1];
+				const uint64_t r = res[j * stride + v0 * 2 + v1];
 				epo_1[0][j] = (int) ((r >> 8) & 255u);
 				epo_1[1][j] = (int) (r & 255u);
 			}
