@@ -773,9 +773,9 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 	const ModeInfo mi = mode_info(p.mode);
 	const ShakeParams sp = single_index_shake_params(p.mode);
 	const int subsets = mi.subsets, ntasks = mi.alpha == 2 ? dual_shape(mi).ntasks : 8 * subsets;
-	// dual-index modes: 16 / 8 tasks per block -- the warp takes 2 / 4 blocks at a time so that the lane = task and
-	// lane = item stages run on full warps
-	const int bpw = mi.alpha == 2 ? 32 / ntasks : 1, wtasks = bpw * ntasks;
+	// modes with 16 / 8 tasks per block (two subsets; dual index) -- the warp takes 2 / 4 blocks at a time so that the
+	// lane = task and lane = item stages run on full warps
+	const int bpw = 32 / ntasks, wtasks = bpw * ntasks;
 	const int sub = (int) lane / ntasks, tk = (int) lane - sub * ntasks; // this lane's task: block of the group, task of the block
 #pragma unroll 1
 	for (;;) {
@@ -795,7 +795,7 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 				build_dual_index_task(ws.task[lane], ws.px[sub], mi, tk, idx_q);
 			} else {
 				const int a = tk / subsets, s = tk - a * subsets;
-				build_single_index_task(ws.task[lane], ws.px[0], subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, idx_q);
+				build_single_index_task(ws.task[lane], ws.px[sub], subsets, p.s.q_top[(size_t) block * 8 + a], s, sp, idx_q);
 			}
 		}
 		{
@@ -821,25 +821,28 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 // window kernel (ep_shaker_2_d, best attempt, packing)
 // =====================================================================================================================
 constexpr int kWinBatch = 32; // work items per batch of the window phase
-// NT tasks per warp; RS = stride of a channel's results in wres (4: one slot per parity combination; 1: the dual-index
-// modes, whose lattices have no parity)
-template <int NT, int RS> struct __align__(16) WindowScratchT {
-	static constexpr int kResStride = RS;
+// NT tasks per warp in NB blocks; wres holds ND channels with RS slots each (4: one per parity combination; 1: the
+// dual-index modes, whose lattices have no parity)
+template <int NT, int RS, int ND, int NB> struct __align__(16) WindowScratchT {
+	static constexpr int kResStride = RS, kBlocks = NB;
 	Task task[NT];
 	uint64_t item_key[kWinBatch];
 	uint64_t item_idx[kWinBatch];
-	uint64_t wres[kWinBatch][4 * RS]; // window_sub_search_u8 results of the batch: [item][channel * RS + pp0 * 2 + pp1]
-	real wepa[kWinBatch][8];          // window_item_fit_u8: least-squares endpoints [endpoint * 4 + channel]
-	uint32_t wsel[kWinBatch][4];      //                     byte-permute selectors
-	ShakeOut so[NT];
-	uint32_t px[NT == kWarpTasks ? 4 : 1][16]; // texels of the warp's blocks
+	union {
+		uint64_t wres[kWinBatch][ND * RS]; // window_sub_search_u8 results of the batch: [item][channel * RS + pp0 * 2 + pp1]
+		ShakeOut so[NT];                   // the tasks' results (after the window phases)
+	};
+	real wepa[kWinBatch][8];             // window_item_fit_u8: least-squares endpoints [endpoint * 4 + channel]
+	uint32_t wsel[kWinBatch][4];         //                     byte-permute selectors
+	uint32_t px[NB][16];                 // texels of the warp's blocks
 	uint8_t item_ti[kWinBatch], item_qp[kWinBatch];
 	uint8_t order[NT];
 	uint8_t same_as[NT]; // first task with the same texels (first_task_with_mask)
-	uint8_t top[8];
+	uint8_t top[NB][8];
 };
-using WindowScratch = WindowScratchT<kMaxTasks, 4>;      // single-index modes: one block per warp
-using WindowScratchDual = WindowScratchT<kWarpTasks, 1>; // dual-index modes: 2 (mode 4) / 4 (mode 5) blocks per warp
+using WindowScratch1 = WindowScratchT<kMaxTasks, 4, 4, 1>;     // modes 0, 2 (24 tasks per block) and 7 (4 channels): one block per warp
+using WindowScratch2 = WindowScratchT<kWarpTasks, 4, 3, 2>;    // modes 1, 3 (16 tasks per block): 2 blocks per warp
+using WindowScratchDual = WindowScratchT<kWarpTasks, 1, 3, 4>; // dual-index modes: 2 (mode 4) / 4 (mode 5) blocks per warp
 
 // Start a round of ep_shaker_2_d for one task (:785-827): collapse, single-index case.
 __device__ __noinline__ void window_begin_round(const Tables &T, Task &t) {
@@ -1083,6 +1086,7 @@ __device__ __forceinline__ void window_group_dual(const AmdParams &p, WindowScra
 		o.idx = t.w_best_idx;
 		o.ep[0] = (uint32_t) t.w_best_ep;
 		o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
+		__syncwarp(); // (so shares its storage with the search results of the phase)
 		ws.so[lane] = o;
 	}
 	__syncwarp();
@@ -1117,103 +1121,113 @@ __device__ __forceinline__ void window_group_dual(const AmdParams &p, WindowScra
 	AMD_T(5);
 }
 
-// One block of a single-index mode (0 .. 3, 7)
-__device__ __forceinline__ void window_block(const AmdParams &p, WindowScratch &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3,
-																						 uint32_t block, unsigned lane) {
-	const BlockCoord bc = block_coord(p, block);
-	if (p.s.q_top[(size_t) block * 8] == 0xffu) { // whole warp: mode not searched for this block
-		if (p.first && lane == 0) {
-			p.dst[bc.gblock] = make_uint4(0, 0, 0, 0);
-			p.best_err[bc.gblock] = A7_HUGE;
-		}
-		return;
-	}
-	__syncwarp();
-	if (lane < 16) ws.px[0][lane] = fetch_rgba_u8(p.img, bc, (int) lane);
-	if (lane < 8) ws.top[lane] = p.s.q_top[(size_t) block * 8 + lane];
-	__syncwarp();
+// A group of WS::kBlocks blocks of a single-index mode (0 .. 3, 7): lane = (block of the group, task of the block)
+template <typename WS>
+__device__ __forceinline__ void window_group_single(const AmdParams &p, WS &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3, uint32_t group,
+																										unsigned lane) {
+	constexpr int bpw = WS::kBlocks;
 	const int mode = p.mode;
 	const ModeInfo mi = mode_info(mode);
 	const ShakeParams sp = single_index_shake_params(mode);
-	const int subsets = mi.subsets, ntasks = 8 * subsets;
+	const int subsets = mi.subsets, ntasks = 8 * subsets, wtasks = bpw * ntasks;
+	const int sub = (int) lane / ntasks, tk = (int) lane - sub * ntasks;
+	const uint32_t block0 = group * (uint32_t) bpw, block = block0 + (uint32_t) sub;
+	const bool present = sub < bpw && block < p.n_blocks;
+	const bool have = present && p.s.q_top[(size_t) block * 8] != 0xffu; // (0xff: mode not searched for this block)
+	if (p.first && present && !have && tk == 0) {
+		p.dst[p.block0 + block] = make_uint4(0, 0, 0, 0);
+		p.best_err[p.block0 + block] = A7_HUGE;
+	}
+	if (!__any_sync(FULL, have)) return;
+	__syncwarp();
+	for (int b = (int) lane >> 4; b < bpw; b += 2) // 16 lanes per block
+		if (block0 + b < p.n_blocks) ws.px[b][lane & 15] = fetch_rgba_u8(p.img, block_coord(p, block0 + b), (int) lane & 15);
+	if ((int) lane < 8 * bpw && block0 + (lane >> 3) < p.n_blocks) ws.top[lane >> 3][lane & 7] = p.s.q_top[(size_t) (block0 + (lane >> 3)) * 8 + (lane & 7)];
+	__syncwarp();
 	const bool cube = sp.dim == 3;
 	const int wtype = sp.bits[3] % (2 * sp.dim);
 	AMD_T0();
-	if ((int) lane < ntasks) {
-		const int a = (int) lane / subsets, s = (int) lane - a * subsets;
+	if (have) {
+		const int a = tk / subsets, s = tk - a * subsets;
 		Task &t = ws.task[lane];
-		const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + lane];
-		build_single_index_task(t, ws.px[0], subsets, ws.top[a], s, sp, idx_q);
+		const uint64_t idx_q = p.s.q_idx[(size_t) block * kMaxTasks + tk];
+		build_single_index_task(t, ws.px[sub], subsets, ws.top[sub][a], s, sp, idx_q);
 		if (cube) {
-			t.best_idx = p.s.c_idx[(size_t) block * kMaxTasks + lane];
-			t.err_o = p.s.c_err[(size_t) block * kMaxTasks + lane];
+			t.best_idx = p.s.c_idx[(size_t) block * kMaxTasks + tk];
+			t.err_o = p.s.c_err[(size_t) block * kMaxTasks + tk];
 		}
 		window_planes_u8(t.d, t.n, t.plane);
 	}
 	{
 		int first = (int) lane;
-		if (subsets == 3) { // (uniform) repeats of a texel set take the first task's result
+		if (subsets == 3) { // (uniform; one block per warp) repeats of a texel set take the first task's result
 			const int a = (int) lane < ntasks ? (int) lane / subsets : 0, s = (int) lane - a * subsets;
-			first = first_task_with_mask(subsets, ws.top[a], s, ntasks, lane);
+			first = first_task_with_mask(subsets, ws.top[0][a], s, ntasks, lane);
 		}
-		if ((int) lane < ntasks) {
+		if ((int) lane < wtasks) {
 			ws.same_as[lane] = (uint8_t) first;
-			if (first != (int) lane) ws.task[lane].w_active = 0;
+			if (!have || first != (int) lane) ws.task[lane].w_active = 0;
 		}
 	}
 	__syncwarp();
 	// shake_subset (:709-805): ep_shaker_2_d on the quantiser's indices and, where ep_shaker_d won, again on its indices
-	window_phase(T, ws, lut2, lut3, ntasks, sp.dim, wtype, lane);
+	window_phase(T, ws, lut2, lut3, wtasks, sp.dim, wtype, lane);
 	AMD_T(3);
 	if (cube) {
-		if ((int) lane < ntasks) {
+		if ((int) lane < wtasks) {
 			Task &t = ws.task[lane];
-			t.w_active = (ws.same_as[lane] == lane && t.err_o < t.w_err_o) ? 1 : 0;
+			t.w_active = (have && ws.same_as[lane] == lane && t.err_o < t.w_err_o) ? 1 : 0;
 			t.w_index = t.best_idx;
 		}
 		__syncwarp();
-		window_phase(T, ws, lut2, lut3, ntasks, sp.dim, wtype, lane);
+		window_phase(T, ws, lut2, lut3, wtasks, sp.dim, wtype, lane);
 		AMD_T(4);
 	}
-	if ((int) lane < ntasks) {
+	ShakeOut o;
+	if ((int) lane < wtasks) {
 		const Task &t = ws.task[ws.same_as[lane]];
-		ShakeOut o;
 		o.err = t.w_err_o;
 		o.idx = t.w_best_idx;
 		o.ep[0] = (uint32_t) t.w_best_ep;
 		o.ep[1] = (uint32_t) (t.w_best_ep >> 32);
-		ws.so[lane] = o;
 	}
+	__syncwarp(); // (so shares its storage with the search results of the phases)
+	if ((int) lane < wtasks) ws.so[lane] = o;
 	__syncwarp();
-	int ba = 0, store = 0;
-	real be = A7_HUGE;
-	if (lane == 0) {
-		for (int a = 0; a < 8; a++) {
-			real e = 0;
-			for (int s = 0; s < subsets; s++) e += ws.so[a * subsets + s].err;
-			if (e < be) { be = e; ba = a; }
-		}
-		const real carried = p.first ? A7_HUGE : p.best_err[bc.gblock];
-		store = (p.first || be < carried) ? 1 : 0;
-	}
-	ba = __shfl_sync(FULL, ba, 0);
-	store = __shfl_sync(FULL, store, 0);
-	if (store) { // (uniform) this mode beats what the earlier modes left in dst
-		uint64_t b0, b1;
-		pack_single_index_warp(mode, ws.top[ba], &ws.so[ba * subsets], lane, b0, b1);
+#pragma unroll 1
+	for (int b = 0; b < bpw; b++) { // (uniform) best attempt of each block, packing
+		if (!__shfl_sync(FULL, have ? 1 : 0, b * ntasks)) continue;
+		const ShakeOut *so = ws.so + b * ntasks;
+		const uint64_t gblock = p.block0 + block0 + (uint32_t) b;
+		int ba = 0, store = 0;
+		real be = A7_HUGE;
 		if (lane == 0) {
-			p.dst[bc.gblock] = make_uint4((uint32_t) b0, (uint32_t) (b0 >> 32), (uint32_t) b1, (uint32_t) (b1 >> 32));
-			p.best_err[bc.gblock] = be;
+			for (int a = 0; a < 8; a++) {
+				real e = 0;
+				for (int s = 0; s < subsets; s++) e += so[a * subsets + s].err;
+				if (e < be) { be = e; ba = a; }
+			}
+			const real carried = p.first ? A7_HUGE : p.best_err[gblock];
+			store = (p.first || be < carried) ? 1 : 0;
+		}
+		ba = __shfl_sync(FULL, ba, 0);
+		store = __shfl_sync(FULL, store, 0);
+		if (store) { // (uniform) this mode beats what the earlier modes left in dst
+			uint64_t b0, b1;
+			pack_single_index_warp(mode, ws.top[b][ba], &so[ba * subsets], lane, b0, b1);
+			if (lane == 0) {
+				p.dst[gblock] = make_uint4((uint32_t) b0, (uint32_t) (b0 >> 32), (uint32_t) b1, (uint32_t) (b1 >> 32));
+				p.best_err[gblock] = be;
+			}
 		}
 	}
 	AMD_T(5);
 }
 
-
 // 8 warps per CTA: 2 CTAs (16 warps) fit the 227 KB of shared memory next to one copy of the ramp tables each
 constexpr int kWindowWarps = 8, kWindowCtasPerSm = 2;
-template <bool DUAL> __global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
-	using WS = typename std::conditional<DUAL, WindowScratchDual, WindowScratch>::type;
+template <typename WS> __global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
+	constexpr bool kDual = std::is_same<WS, WindowScratchDual>::value;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WS *scratch = reinterpret_cast<WS *>(smem_raw);
 	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
@@ -1223,17 +1237,20 @@ template <bool DUAL> __global__ void __launch_bounds__(kWindowWarps * 32, kWindo
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 	WS &ws = scratch[warp];
 	const Tables T{p.sp};
-	const uint32_t units = DUAL ? (p.n_blocks + (p.mode == 4 ? 1u : 3u)) / (p.mode == 4 ? 2u : 4u) : p.n_blocks; // blocks, or groups of 2 / 4 blocks
+	const uint32_t bpw = kDual ? (p.mode == 4 ? 2u : 4u) : (uint32_t) WS::kBlocks;
+	const uint32_t groups = (p.n_blocks + bpw - 1) / bpw;
 #pragma unroll 1
 	for (;;) {
-		const uint32_t unit = fetch_block(p.next_block, lane);
-		if (unit >= units) break;
-		if constexpr (DUAL) window_group_dual(p, ws, T, lut2, lut3, unit, lane);
-		else window_block(p, ws, T, lut2, lut3, unit, lane);
+		const uint32_t group = fetch_block(p.next_block, lane);
+		if (group >= groups) break;
+		if constexpr (kDual) window_group_dual(p, ws, T, lut2, lut3, group, lane);
+		else window_group_single(p, ws, T, lut2, lut3, group, lane);
 	}
 }
 // (2 CTAs of 8 warps and their tables fit the shared memory of an SM)
-static_assert(kWindowWarps * sizeof(WindowScratch) + 6144 + 1024 <= 116736 && kWindowWarps * sizeof(WindowScratchDual) + 6144 + 1024 <= 116736, "window scratch: 2 CTAs per SM");
+constexpr size_t kWindowSmemBudget = (233472 / kWindowCtasPerSm - 1024 - 6144) / kWindowWarps;
+static_assert(sizeof(WindowScratch1) <= kWindowSmemBudget && sizeof(WindowScratch2) <= kWindowSmemBudget && sizeof(WindowScratchDual) <= kWindowSmemBudget,
+							"window scratch: 2 CTAs per SM");
 
 // =====================================================================================================================
 // Modes with few independent tasks per block -- mode 6: ONE partition, ONE subset; modes 4 / 5: 16 / 8 (rotation,
@@ -1587,9 +1604,11 @@ cudaError_t init_bc7amd_tables() {
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(amd_quant_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(DualQuantScratch)));
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch)));
+	e = cudaFuncSetAttribute(amd_window_kernel<WindowScratch1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch1)));
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratchDual)));
+	e = cudaFuncSetAttribute(amd_window_kernel<WindowScratch2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch2)));
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(amd_window_kernel<WindowScratchDual>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratchDual)));
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(bc7amd_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(FloatScratch)));
 	if (e != cudaSuccess) return e;
@@ -1687,8 +1706,9 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 				{
 					ProfScope ps(stream, mode, 2);
 					p.next_block = counter++;
-					if (mode == 4 || mode == 5) amd_window_kernel<true><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratchDual), stream>>>(p);
-					else amd_window_kernel<false><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch), stream>>>(p);
+					if (mode == 4 || mode == 5) amd_window_kernel<WindowScratchDual><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratchDual), stream>>>(p);
+					else if (mode == 1 || mode == 3) amd_window_kernel<WindowScratch2><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch2), stream>>>(p);
+					else amd_window_kernel<WindowScratch1><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch1), stream>>>(p);
 				}
 				launches += mode != 7 ? 3 : 2;
 			}
