@@ -737,6 +737,7 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 		}
 		__syncwarp();
 		// ---- per task: the reference's change / better logic (:1372-1400)
+		if ((int) lane < ntasks && !ws.task[lane].done && ws.task[lane].pass_key == ~0ull) ws.task[lane].done = 1; // pruned pass: nothing could beat the first pass
 		if ((int) lane < ntasks && !ws.task[lane].done) {
 			Task &t = ws.task[lane];
 			const real err_2 = (real) (uint32_t) (t.pass_key >> 16);

@@ -521,12 +521,13 @@ A7_HD int qp_count(int Mi, int Mi_) {
 	for (int q = 1; q * Mi <= Mi_; q++) c += Mi_ - q * Mi + 1;
 	return c;
 }
-A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) {
+A7_HD void qp_decode(int ord, int Mi, int Mi_, int &q, int &p) { // (ord < qp_count(Mi, Mi_); anything else ends at the last q)
+	p = ord;
 #pragma unroll 1
-	for (q = 1;; q++) {
+	for (q = 1; (q + 1) * Mi <= Mi_; q++) {
 		const int cnt = Mi_ - q * Mi + 1;
-		if (ord < cnt) { p = ord; return; }
-		ord -= cnt;
+		if (p < cnt) return;
+		p -= cnt;
 	}
 }
 // One work item of ep_shaker_d: texels d[], collapsed indices (4 bits each), one (q, p), z-slices [z0, z1) of every
