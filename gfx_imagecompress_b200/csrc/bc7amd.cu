@@ -332,16 +332,20 @@ template <typename WS> __device__ __forceinline__ int item_owner(const WS &ws, i
 // quantise kernel
 // =====================================================================================================================
 struct QuantScratch {
-	float in[64];
-	BlockInput B;
+	real pxc[4][16];      // the block, channel-major, 0..255 (quantiser input, see QuantIO)
 	real serr[64][3];
 	uint64_t qidx[64][3]; // quantiser indices of every (partition, subset) of the running mode
-	real perr[64];
+	union {
+		real qs[2][15][32]; // the two lane-strided FP64 work arrays of QuantIO (element k of lane l at [k][l]); a subset has <= 15 texels
+		real perr[64];      // (after the quantiser rounds) error per partition
+	};
+	uint32_t mode_mask;   // after the filter of :1340-1380
 	int top[8];
-	real qs[2][16][32];   // the two lane-strided FP64 work arrays of QuantIO (element k of lane l at [k][l])
 };
+constexpr int kQuantCtasPerSm = 5;
+static_assert(kWarps * sizeof(QuantScratch) <= 233472 / kQuantCtasPerSm - 1024, "quantise scratch: 5 CTAs per SM");
 
-__global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdParams p) {
+__global__ void __launch_bounds__(kWarps * 32, kQuantCtasPerSm) amd_quant_kernel(const AmdParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	QuantScratch *scratch = reinterpret_cast<QuantScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -349,23 +353,18 @@ __global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdPara
 	if (block >= p.n_blocks) return; // whole warp
 	QuantScratch &ws = scratch[warp];
 	const BlockCoord bc = block_coord(p, block);
-	if (lane < 16) {
-		const float4 t = fetch_rgba(p.img, bc.gblock, bc.bx, bc.by, bc.slice, (int) lane);
-		ws.in[lane * 4 + 0] = t.x; ws.in[lane * 4 + 1] = t.y; ws.in[lane * 4 + 2] = t.z; ws.in[lane * 4 + 3] = t.w;
-	}
-	__syncwarp();
 	{ // prepare_block (bc7amd_core.cuh) with one texel per lane
 		bool na = false, zo = false;
 		real v[4] = {0, 0, 0, 0};
 		if (lane < 16) {
-			const float a = ws.in[lane * 4 + 3];
-			if (a < 1.0) na = true;
-			else if (((double) a >= 0.99999) || ((double) a < 0.00001)) zo = true;
+			const float4 t = fetch_rgba(p.img, bc.gblock, bc.bx, bc.by, bc.slice, (int) lane);
+			const float in4[4] = {t.x, t.y, t.z, t.w};
+			if (t.w < 1.0) na = true;
+			else if (((double) t.w >= 0.99999) || ((double) t.w < 0.00001)) zo = true;
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
-				v[j] = (real) (ws.in[lane * 4 + j] * 255.0f);
-				ws.B.px[lane][j] = v[j];
-				ws.B.pxc[j][lane] = v[j];
+				v[j] = (real) (in4[j] * 255.0f);
+				ws.pxc[j][lane] = v[j];
 			}
 		}
 		const bool needs_alpha = __any_sync(FULL, na), zero_one = __any_sync(FULL, zo);
@@ -382,11 +381,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdPara
 			const real r = mx - mn;
 			range = j == 0 ? r : (range > r ? range : r);
 		}
-		if (lane == 0) ws.B.mode_mask = filter_modes(p.mode_mask, needs_alpha, zero_one, range < 1e-10);
+		if (lane == 0) ws.mode_mask = filter_modes(p.mode_mask, needs_alpha, zero_one, range < 1e-10);
 	}
 	__syncwarp();
 	const int mode = p.mode;
-	if (!(ws.B.mode_mask & p.launch_modes & (1u << mode))) { // whole warp
+	if (!(ws.mode_mask & p.launch_modes & (1u << mode))) { // whole warp
 		if (lane == 0) p.s.q_top[(size_t) block * 8] = 0xffu;
 		return;
 	}
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) amd_quant_kernel(const AmdPara
 	const int nparts = 1 << mi.partition_bits, subsets = mi.subsets;
 	const uint8_t *qorder = quantise_order(subsets, nparts);
 	QuantIOShared io;
-	io.px = (uint32_t) __cvta_generic_to_shared(&ws.B.pxc[0][0]);
+	io.px = (uint32_t) __cvta_generic_to_shared(&ws.pxc[0][0]);
 	io.chan = 0xE4u;
 	io.proj = (uint32_t) __cvta_generic_to_shared(&ws.qs[0][0][lane]);
 	io.dev = (uint32_t) __cvta_generic_to_shared(&ws.qs[1][0][lane]);
