@@ -263,7 +263,12 @@ struct QuantIOShared {
 		return v;
 	}
 	static __device__ __forceinline__ void sts(uint32_t a, real v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-	__device__ __forceinline__ real point(uint32_t idx) const { return lds(px + idx * 8u); }
+	static __device__ __forceinline__ real lds_const(uint32_t a) { // the block's texels do not change during a call: the compiler may move / merge these loads
+		real v;
+		asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+		return v;
+	}
+	__device__ __forceinline__ real point(uint32_t idx) const { return lds_const(px + idx * 8u); }
 	__device__ __forceinline__ real get_proj(int i) const { return lds(proj + (uint32_t) (i * stride) * 8u); }
 	__device__ __forceinline__ void set_proj(int i, real v) const { sts(proj + (uint32_t) (i * stride) * 8u, v); }
 	__device__ __forceinline__ real get_dev(int i) const { return lds(dev + (uint32_t) (i * stride) * 8u); }
