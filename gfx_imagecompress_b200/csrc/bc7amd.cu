@@ -48,6 +48,10 @@ __constant__ uint8_t c_qorder[48 + 192 + 128];
 __device__ __forceinline__ const uint8_t *quantise_order(int subsets, int nparts) {
 	return subsets == 3 ? (nparts == 16 ? c_qorder : c_qorder + 48) : c_qorder + 240;
 }
+// The 3-subset tables repeat subsets (36 distinct texel masks among the 48 of mode 0, 140 among the 192 of mode 2) and the
+// quantiser is a pure function of the texel list: c_qfirst[order position] = the first position (same table, same order)
+// with that mask; only those are quantised, the repeats copy.  The 2-subset masks are all distinct.
+__constant__ uint8_t c_qfirst[48 + 192];
 
 // Optional phase timing (build with -DB200IC_AMD_TIMING, read with b200ic_amd_timing): clock64 deltas of lane 0 summed
 // per phase over all warps. Slots: 0 quantise, 1 rank, 2 cube, 3 window, 4 window (2nd), 5 pick+pack,
@@ -400,7 +404,16 @@ __global__ void __launch_bounds__(kWarps * 32, kQuantCtasPerSm) amd_quant_kernel
 	io.proj = (uint32_t) __cvta_generic_to_shared(&ws.qs[0][0][lane]);
 	io.dev = (uint32_t) __cvta_generic_to_shared(&ws.qs[1][0][lane]);
 	io.stride = 32;
-	for (int tt = (int) lane; tt < nparts * subsets; tt += 32) {
+	// the distinct subsets come first in the order (sorted by size among themselves), the repeats after them
+	const uint8_t *qfirst = subsets == 3 ? (nparts == 16 ? c_qfirst : c_qfirst + 48) : nullptr;
+	const int nproblems = nparts * subsets;
+	int ndistinct = nproblems;
+	if (qfirst) {
+		ndistinct = 0;
+		for (int tt = (int) lane; tt < nproblems; tt += 32) ndistinct += qfirst[tt] == tt ? 1 : 0;
+		ndistinct = __reduce_add_sync(FULL, ndistinct);
+	}
+	for (int tt = (int) lane; tt < ndistinct; tt += 32) {
 		const int t = qorder[tt];
 		const int part = t / subsets, s = t - part * subsets;
 		uint32_t smask = 0;
@@ -410,6 +423,12 @@ __global__ void __launch_bounds__(kWarps * 32, kQuantCtasPerSm) amd_quant_kernel
 		uint64_t packed = 0;
 		ws.serr[part][s] = n ? quantise_subset(io, n, sp.clusters, sp.dim, packed) : 0;
 		ws.qidx[part][s] = packed;
+	}
+	__syncwarp();
+	for (int tt = ndistinct + (int) lane; tt < nproblems; tt += 32) { // repeats
+		const int t = qorder[tt], f = qorder[qfirst[tt]];
+		ws.serr[t / subsets][t % subsets] = ws.serr[f / subsets][f % subsets];
+		ws.qidx[t / subsets][t % subsets] = ws.qidx[f / subsets][f % subsets];
 	}
 	__syncwarp();
 	AMD_T(0);
@@ -1578,18 +1597,37 @@ cudaError_t init_bc7amd_tables() {
 	e = cudaMemcpy(d, host, kSpEntries * sizeof(uint32_t), cudaMemcpyHostToDevice);
 	if (e != cudaSuccess) return e;
 	{
-		uint8_t order[48 + 192 + 128];
+		uint8_t order[48 + 192 + 128], first[48 + 192];
 		int pos = 0;
 		for (int table = 0; table < 3; table++) {
-			const int subsets = table < 2 ? 3 : 2, nparts = table == 0 ? 16 : 64;
-			for (int size = 16; size >= 0; size--)
-				for (int t = 0; t < nparts * subsets; t++) {
-					const int part = t / subsets, s = t % subsets;
-					int n = 0;
-					for (int i = 0; i < 16; i++) n += subset_of(subsets, part, i) == s ? 1 : 0;
-					if (n == size) order[pos++] = (uint8_t) t;
+			const int subsets = table < 2 ? 3 : 2, nparts = table == 0 ? 16 : 64, base = pos;
+			auto mask_of = [&](int t) {
+				uint32_t m = 0;
+				for (int i = 0; i < 16; i++) m |= (subset_of(subsets, t / subsets, i) == t % subsets ? 1u : 0u) << i;
+				return m;
+			};
+			auto repeats = [&](int t) { // an earlier (partition, subset) of the table has the same texels
+				for (int u = 0; u < t; u++)
+					if (mask_of(u) == mask_of(t)) return true;
+				return false;
+			};
+			for (int rep = 0; rep < 2; rep++) // the distinct subsets first, then the repeats; each part by size, descending
+				for (int size = 16; size >= 0; size--)
+					for (int t = 0; t < nparts * subsets; t++) {
+						int n = 0;
+						for (int i = 0; i < 16; i++) n += subset_of(subsets, t / subsets, i) == t % subsets ? 1 : 0;
+						if (n == size && (repeats(t) ? 1 : 0) == rep) order[pos++] = (uint8_t) t;
+					}
+			if (table < 2)
+				for (int i = base; i < pos; i++) {
+					int f = i;
+					for (int j = base; j < i; j++)
+						if (mask_of(order[j]) == mask_of(order[i])) { f = j; break; }
+					first[i] = (uint8_t) (f - base);
 				}
 		}
+		e = cudaMemcpyToSymbol(c_qfirst, first, sizeof(first));
+		if (e != cudaSuccess) return e;
 		e = cudaMemcpyToSymbol(c_qorder, order, sizeof(order));
 		if (e != cudaSuccess) return e;
 	}
