@@ -225,6 +225,7 @@ B7_HDN void evaluate(const Cell &cell, uint32_t lo, uint32_t hi, const uint32_t 
 		const int dr = (int) ch(ahi, 0) - lr, dg = (int) ch(ahi, 1) - lg, db = (int) ch(ahi, 2) - lb, da = (int) ch(ahi, 3) - la;
 		const float f = ALPHA ? (float) N / (float) ((float) (dr * dr + dg * dg + db * db + da * da) + .00000125f)
 													: (float) N / (float) ((float) (dr * dr + dg * dg + db * db) + .00000125f);
+		#pragma unroll 1
 		for (int i = 0; i < cell.n; i++) {
 			const uint32_t c = cell.px[i];
 			int proj = ((int) ch(c, 0) - lr) * dr + ((int) ch(c, 1) - lg) * dg + ((int) ch(c, 2) - lb) * db;
@@ -249,6 +250,7 @@ B7_HDN void evaluate(const Cell &cell, uint32_t lo, uint32_t hi, const uint32_t 
 			pcb[j] = (b << 9) - pl_[j];
 			pa[j] = (int) ch(pal[j], 3);
 		}
+		#pragma unroll 1
 		for (int i = 0; i < cell.n; i++) {
 			const uint32_t c = cell.px[i];
 			const int r = (int) ch(c, 0), g = (int) ch(c, 1), b = (int) ch(c, 2), a = (int) ch(c, 3);
@@ -282,7 +284,7 @@ B7_HDN void evaluate(const Cell &cell, uint32_t lo, uint32_t hi, const uint32_t 
 // find_optimal_solution (:606-729) for the p-bit modes (1 and 6 both carry p-bits): round the float endpoints
 // to each p-bit lattice, keep the closer, fix degenerate mode-1 channels, evaluate unless it is the current best.
 template <int MODE, bool ALPHA>
-B7_HD uint64_t try_endpoints(const Cell &cell, F4 xl, F4 xh, const Params &P, Best &best) {
+B7_HDN uint64_t try_endpoints(const Cell &cell, F4 xl, F4 xh, const Params &P, Best &best) {
 #pragma unroll
 	for (int c = 0; c < 4; c++) { xl.v[c] = sat(xl.v[c]); xh.v[c] = sat(xh.v[c]); }
 	constexpr int iscalep = (1 << (ModeTraits<MODE>::kCompBits + 1)) - 1;
@@ -353,10 +355,11 @@ B7_HD uint64_t try_endpoints(const Cell &cell, F4 xl, F4 xh, const Params &P, Be
 
 // compute_least_squares_endpoints_rgb[a] (:197-280), result already scaled by 1/255 (:889-890)
 template <int MODE, bool ALPHA>
-B7_HD void least_squares(const Cell &cell, uint64_t sels, F4 &xl, F4 &xh) {
+B7_HDN void least_squares(const Cell &cell, uint64_t sels, F4 &xl, F4 &xh) {
 	float z00 = 0.f, z10 = 0.f, z11 = 0.f;
 	float q00[4] = {0.f, 0.f, 0.f, 0.f}, t[4] = {0.f, 0.f, 0.f, 0.f};
 	constexpr int NC = ALPHA ? 4 : 3;
+	#pragma unroll 1
 	for (int i = 0; i < cell.n; i++) {
 		const uint32_t s = sel_get(sels, i);
 		const float *wx = (ModeTraits<MODE>::kSelectors == 16) ? kLsq4[s] : kLsq3[s];
@@ -402,6 +405,7 @@ B7_HD uint64_t single_colour_mode1(const Cell &cell, uint32_t r, uint32_t g, uin
 	out.pbit[0] = bp;
 	out.pbit[1] = 0;
 	uint64_t sels = 0;
+	#pragma unroll 1
 	for (int i = 0; i < cell.n; i++) sels |= sel_put(2, i);
 	out.sel = sels;
 	uint32_t pc = 255u << 24;
@@ -414,6 +418,7 @@ B7_HD uint64_t single_colour_mode1(const Cell &cell, uint32_t r, uint32_t g, uin
 		pc |= (((lo * (64 - 18) + hi * 18 + 32) >> 6) & 255u) << (8 * c);
 	}
 	uint64_t total = 0;
+	#pragma unroll 1
 	for (int i = 0; i < cell.n; i++) total += dist_rgb(pc, cell.px[i], P, P.perceptual != 0);
 	out.err = total;
 	return total;
@@ -431,10 +436,12 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 	if (MODE == 1) {
 		const uint32_t rgb0 = cell.px[0] & 0xffffffu;
 		bool same = true;
+		#pragma unroll 1
 		for (int i = 1; i < n; i++) same = same && ((cell.px[i] & 0xffffffu) == rgb0);
 		if (same) return single_colour_mode1(cell, ch(rgb0, 0), ch(rgb0, 1), ch(rgb0, 2), P, best);
 	}
 	F4 sum = {{0.f, 0.f, 0.f, 0.f}};
+	#pragma unroll 1
 	for (int i = 0; i < n; i++) {
 #pragma unroll
 		for (int c = 0; c < 4; c++) sum.v[c] = sum.v[c] + (float) (int) ch(cell.px[i], c);
@@ -448,6 +455,7 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 	}
 	F4 axis = {{0.f, 0.f, 0.f, 0.f}};
 	if (ALPHA) { // incremental PCA (:771-791)
+		#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			F4 col;
 #pragma unroll
@@ -465,6 +473,7 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 		normalise(axis);
 	} else { // covariance + 3 power iterations (:795-832)
 		float cov[6] = {0, 0, 0, 0, 0, 0};
+		#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			const float r = (float) (int) ch(cell.px[i], 0) - mean_s.v[0];
 			const float g = (float) (int) ch(cell.px[i], 1) - mean_s.v[1];
@@ -496,6 +505,7 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 		normalise(axis);
 	}
 	float l = 1e+9f, h = -1e+9f;
+	#pragma unroll 1
 	for (int i = 0; i < n; i++) {
 		F4 q;
 #pragma unroll
@@ -523,6 +533,7 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 	if (P.uber > 0) { // :896-1007
 		const uint64_t base = best.sel;
 		uint32_t smin = 16, smax = 0;
+		#pragma unroll 1
 		for (int i = 0; i < n; i++) {
 			const uint32_t s = sel_get(base, i);
 			smin = s < smin ? s : smin;
@@ -530,6 +541,7 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 		}
 		for (int variant = 0; variant < 3; variant++) { // raise the lowest, lower the highest, both
 			uint64_t t = 0;
+			#pragma unroll 1
 			for (int i = 0; i < n; i++) {
 				uint32_t s = sel_get(base, i);
 				if (variant != 1 && s == smin && s < (uint32_t) (N - 1)) s++;
@@ -547,6 +559,7 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 				for (int hy = top - 1; hy <= top + Q; hy++) {
 					if (ly == 0 && hy == top) continue;
 					uint64_t t = 0;
+					#pragma unroll 1
 					for (int i = 0; i < n; i++) {
 						float v = floorf((float) top * ((float) sel_get(base, i) - (float) ly) / ((float) hy - (float) ly) + .5f);
 						v = v < 0.f ? 0.f : (v > (float) top ? (float) top : v);
@@ -568,9 +581,9 @@ B7_HDN uint64_t compress_cell(const Cell &cell, const Params &P, Best &best) {
 }
 
 // color_cell_compression_est (:1026-1162) evaluated completely (no early-out): bounding-box diagonal, 8-point ramp
-B7_HD uint64_t estimate_subset(const uint32_t *px, uint32_t mask, const Params &P) {
+B7_HDN uint64_t estimate_subset(const uint32_t *px, uint32_t mask, const Params &P) {
 	uint32_t lo[3] = {255, 255, 255}, hi[3] = {0, 0, 0};
-#pragma unroll
+#pragma unroll 1
 	for (int i = 0; i < 16; i++)
 		if ((mask >> i) & 1u) {
 #pragma unroll
@@ -593,7 +606,7 @@ B7_HD uint64_t estimate_subset(const uint32_t *px, uint32_t mask, const Params &
 #pragma unroll
 	for (int j = 0; j < 7; j++) thr[j] = (dots[j] + dots[j + 1] + 1) >> 1;
 	uint64_t total = 0;
-#pragma unroll
+#pragma unroll 1
 	for (int i = 0; i < 16; i++)
 		if ((mask >> i) & 1u) {
 			const int r = (int) ch(px[i], 0), g = (int) ch(px[i], 1), b = (int) ch(px[i], 2);
