@@ -578,7 +578,7 @@ __device__ __forceinline__ void cube_finish_task(Task &t, uint64_t lane_best, co
 
 // All corners of one item, one per lane; folds the item's best into the lane's running best of the task.
 template <int CLOG>
-__device__ __forceinline__ void cube_item_corners(const CubeScratch &ws, const uint32_t (&d)[16], int n, int nlb, int qp, unsigned lane, uint64_t &lane_best,
+__device__ __forceinline__ void cube_item_corners(const CubeScratch &ws, const uint32_t *d, int n, int nlb, int qp, unsigned lane, uint64_t &lane_best,
 																									uint32_t *best_pal) {
 	uint32_t key, xy;
 	cube_lane_corners<CLOG>(ws.tab, d, n, nlb, lane, key, xy);
@@ -593,7 +593,7 @@ __device__ __forceinline__ void cube_item_corners(const CubeScratch &ws, const u
 // 12 bounds per lattice over the lanes, the corners whose bound does not exceed `thr` compacted into a list (ballot-free:
 // per-lane masks + prefix sum), one surviving corner per lane and round.  thr follows the best error found.
 template <int CLOG>
-__device__ __forceinline__ void cube_item_pruned(CubeScratch &ws, const uint32_t (&d)[16], int n, int nlb, int qp, unsigned lane, uint32_t &thr,
+__device__ __forceinline__ void cube_item_pruned(CubeScratch &ws, const uint32_t *d, int n, int nlb, int qp, unsigned lane, uint32_t &thr,
 																								 uint64_t &lane_best, uint32_t *best_pal) {
 	constexpr int C = 1 << CLOG;
 	const int nl = 1 << nlb;
@@ -640,8 +640,16 @@ __device__ __forceinline__ void cube_item_pruned(CubeScratch &ws, const uint32_t
 	thr = umin32(thr, __reduce_min_sync(FULL, item_min));
 }
 
+// The index widths a launch can meet (CLOGS: bit 2 = 2-bit, bit 3 = 3-bit indices) are a property of the mode; only the
+// dual-index mode 4 has both.  The code of the other width is compiled out: the cube and window kernels stall on
+// instruction fetch more than on anything else when their loop bodies do not fit the instruction caches.
+template <int CLOGS> __device__ __forceinline__ bool is_clog2(int clog) { return CLOGS == 4 || (CLOGS == 12 && clog == 2); }
+__host__ __device__ constexpr int mode_clogs(int mode) { return mode == 4 ? 12 : ((mode == 0 || mode == 1) ? 8 : 4); }
+
 // ep_shaker_d for all tasks of the warp. On return task[i].err_o / best_idx hold its result.
-__device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, bool prune2, unsigned lane) {
+template <int CLOGS, bool PRUNE2>
+__device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, unsigned lane) {
+	constexpr bool prune2 = PRUNE2;
 	if ((int) lane < ntasks) {
 		Task &t = ws.task[lane];
 		t.err_o = A7_HUGE;
@@ -666,9 +674,7 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 		int cur_ti = -1, n = 0, clog = 3, nlb = 0, bcc = 0;
 		uint32_t thr = 0xffffffffu; // second pass: what a corner has to beat (the first pass's error - 1, then the best found)
 		const bool prune = prune2 && pass == 1;
-		uint32_t d[16];
-#pragma unroll
-		for (int i = 0; i < 16; i++) d[i] = 0;
+		const uint32_t *d = ws.task[0].d; // texels of the running task (shared memory: the lanes read them together)
 		uint64_t lane_best = ~0ull;
 		uint32_t best_pal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
@@ -684,7 +690,7 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 					qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
 					const int use_par = (t.type == BCC || t.type == SAME_PAR) ? 1 : 0;
 					uint32_t ep[6];
-					if (t.clog == 2) cube_item_setup_u8<2>(t.d, t.n, t.cur, q, p, t.bits, use_par, ep);
+					if (is_clog2<CLOGS>(t.clog)) cube_item_setup_u8<2>(t.d, t.n, t.cur, q, p, t.bits, use_par, ep);
 					else cube_item_setup_u8<3>(t.d, t.n, t.cur, q, p, t.bits, use_par, ep);
 #pragma unroll
 					for (int k = 0; k < 6; k++) ws.item_ep[lane][k] = ep[k];
@@ -699,16 +705,11 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 				const int ti = ws.item_ti[j];
 				if (ti != cur_ti) { // (uniform) next task: close the previous one, take the new texels into registers
 					if (cur_ti >= 0) {
-						if (clog == 2) cube_finish_task<2>(ws.task[cur_ti], lane_best, best_pal, lane);
+						if (is_clog2<CLOGS>(clog)) cube_finish_task<2>(ws.task[cur_ti], lane_best, best_pal, lane);
 						else cube_finish_task<3>(ws.task[cur_ti], lane_best, best_pal, lane);
 					}
 					const Task &t = ws.task[ti];
-					const uint4 *dv = reinterpret_cast<const uint4 *>(t.d);
-#pragma unroll
-					for (int v = 0; v < 4; v++) {
-						const uint4 w = dv[v];
-						d[4 * v + 0] = w.x; d[4 * v + 1] = w.y; d[4 * v + 2] = w.z; d[4 * v + 3] = w.w;
-					}
+					d = t.d;
 					n = t.n;
 					clog = t.clog;
 					bcc = t.type == BCC ? 1 : 0;
@@ -731,7 +732,7 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 				{
 					const uint32_t *ep = ws.item_ep[j];
 					uint32_t *tw = reinterpret_cast<uint32_t *>(ws.tab);
-					if (clog == 2) {
+					if (is_clog2<CLOGS>(clog)) {
 						for (int id = (int) lane; id < (12 << nlb); id += 32) tw[2 * id] = cube_tab_word_lut<2>(lut2, ep, bcc, id);
 					} else {
 						for (int id = (int) lane; id < (24 << nlb); id += 32) tw[id] = cube_tab_word_lut<3>(lut3, ep, bcc, id);
@@ -740,17 +741,17 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 				__syncwarp();
 				const int qp = ws.item_qp[j];
 				if (prune) {
-					if (clog == 2) cube_item_pruned<2>(ws, d, n, nlb, qp, lane, thr, lane_best, best_pal);
+					if (is_clog2<CLOGS>(clog)) cube_item_pruned<2>(ws, d, n, nlb, qp, lane, thr, lane_best, best_pal);
 					else cube_item_pruned<3>(ws, d, n, nlb, qp, lane, thr, lane_best, best_pal);
 				} else {
-					if (clog == 2) cube_item_corners<2>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
+					if (is_clog2<CLOGS>(clog)) cube_item_corners<2>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
 					else cube_item_corners<3>(ws, d, n, nlb, qp, lane, lane_best, best_pal);
 				}
 				__syncwarp();
 			}
 		}
 		if (cur_ti >= 0) {
-			if (clog == 2) cube_finish_task<2>(ws.task[cur_ti], lane_best, best_pal, lane);
+			if (is_clog2<CLOGS>(clog)) cube_finish_task<2>(ws.task[cur_ti], lane_best, best_pal, lane);
 			else cube_finish_task<3>(ws.task[cur_ti], lane_best, best_pal, lane);
 		}
 		__syncwarp();
@@ -780,11 +781,11 @@ __device__ __forceinline__ void cube_phase(const Tables &T, CubeScratch &ws, con
 // Persistent: one CTA per resident slot, every warp takes the next block of the chunk from the launch's counter; the two
 // difference tables of the ramps (6 KB, bc7amd_int.cuh) are built once per CTA.
 constexpr int kCubeCtasPerSm = 5;
-__global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(const AmdParams p) {
+template <int CLOGS, bool PRUNE2> __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(const AmdParams p) {
 	__shared__ CubeScratch scratch[kWarps];
 	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
-	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWarps * 32);
-	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWarps * 32);
+	if (CLOGS & 4) ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWarps * 32);
+	if (CLOGS & 8) ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWarps * 32);
 	__syncthreads();
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 	CubeScratch &ws = scratch[warp];
@@ -826,7 +827,7 @@ __global__ void __launch_bounds__(kWarps * 32, kCubeCtasPerSm) amd_cube_kernel(c
 			if ((int) lane < wtasks) ws.same_as[lane] = (uint8_t) first;
 		}
 		__syncwarp();
-		cube_phase(T, ws, lut2, lut3, wtasks, p.mode == 0, lane); // (second-pass pruning pays where an item has 256 corners: mode 0; mode 2 with 64 measured 2x slower)
+		cube_phase<CLOGS, PRUNE2>(T, ws, lut2, lut3, wtasks, lane);
 		if (have) {
 			const Task &t = ws.task[ws.same_as[lane]];
 			p.s.c_idx[(size_t) block * kMaxTasks + tk] = t.best_idx;
@@ -891,7 +892,7 @@ __device__ __noinline__ void window_begin_round(const Tables &T, Task &t) {
 }
 
 // ep_shaker_2_d for the tasks with w_active set, starting from task.w_index. Results in w_err_o / w_best_idx / w_best_ep.
-template <typename WS>
+template <int CLOGS, typename WS>
 __device__ __noinline__ void window_phase(const Tables &T, WS &ws, const uint32_t *lut2, const uint32_t *lut3, int ntasks, int dim, int type, unsigned lane) {
 	if ((int) lane < ntasks) {
 		Task &t = ws.task[lane];
@@ -931,7 +932,7 @@ __device__ __noinline__ void window_phase(const Tables &T, WS &ws, const uint32_
 				qp_decode(qp, t.Mi, (1 << t.clog) - 1, q, p);
 				real epa[8];
 				uint32_t sel[4];
-				if (t.clog == 2) window_item_fit_u8<2>(t.d, t.n, t.cur, q, p, dim, epa, sel);
+				if (is_clog2<CLOGS>(t.clog)) window_item_fit_u8<2>(t.d, t.n, t.cur, q, p, dim, epa, sel);
 				else window_item_fit_u8<3>(t.d, t.n, t.cur, q, p, dim, epa, sel);
 #pragma unroll
 				for (int k = 0; k < 8; k++) ws.wepa[lane][k] = epa[k];
@@ -950,7 +951,7 @@ __device__ __noinline__ void window_phase(const Tables &T, WS &ws, const uint32_
 				const uint4 pv = *reinterpret_cast<const uint4 *>(t.plane + 4 * j);
 				const uint32_t sel[4] = {sv.x, sv.y, sv.z, sv.w}, plw[4] = {pv.x, pv.y, pv.z, pv.w};
 				const real ep0 = ws.wepa[item][j], ep1 = ws.wepa[item][4 + j];
-				ws.wres[item][j * WS::kResStride + pp0 * 2 + pp1] = t.clog == 2 ? window_sub_search_u8<2>(lut2, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1)
+				ws.wres[item][j * WS::kResStride + pp0 * 2 + pp1] = is_clog2<CLOGS>(t.clog) ? window_sub_search_u8<2>(lut2, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1)
 																													 : window_sub_search_u8<3>(lut3, ep0, ep1, sel, plw, t.n, mb, use_par, t.w_size, pp0, pp1);
 			}
 			__syncwarp();
@@ -980,7 +981,7 @@ __device__ __noinline__ void window_phase(const Tables &T, WS &ws, const uint32_
 			const int mb = (t.w_bits_total + 2 * t.dim - 1) / (2 * t.dim);
 			uint64_t idg;
 			uint32_t err_r;
-			if (t.clog == 2) err_r = recluster_u8<2>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
+			if (is_clog2<CLOGS>(t.clog)) err_r = recluster_u8<2>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
 			else err_r = recluster_u8<3>(t.d, t.n, t.pass_idx, mb, t.dim, idg);
 			int change = 0;
 			for (int k = 0; k < t.n; k++) change = change || ((int) ((t.cur >> (4 * k)) & 15u) * q0 + p0 != (int) ((idg >> (4 * k)) & 15u));
@@ -1063,6 +1064,7 @@ __device__ __forceinline__ void pack_single_index_warp(int mode, int partition, 
 }
 
 // A group of 2 / 4 blocks of a dual-index mode (4 / 5): lane = (block of the group, task of the block)
+template <int CLOGS>
 __device__ __forceinline__ void window_group_dual(const AmdParams &p, WindowScratchDual &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3,
 																									uint32_t group, unsigned lane) {
 	const int mode = p.mode;
@@ -1096,7 +1098,7 @@ __device__ __forceinline__ void window_group_dual(const AmdParams &p, WindowScra
 		}
 	}
 	__syncwarp();
-	window_phase(T, ws, lut2, lut3, kWarpTasks, 3, CART, lane);
+	window_phase<CLOGS>(T, ws, lut2, lut3, kWarpTasks, 3, CART, lane);
 	AMD_T(3);
 	{
 		const Task &t = ws.task[lane];
@@ -1141,7 +1143,7 @@ __device__ __forceinline__ void window_group_dual(const AmdParams &p, WindowScra
 }
 
 // A group of WS::kBlocks blocks of a single-index mode (0 .. 3, 7): lane = (block of the group, task of the block)
-template <typename WS>
+template <int CLOGS, typename WS>
 __device__ __forceinline__ void window_group_single(const AmdParams &p, WS &ws, const Tables &T, const uint32_t *lut2, const uint32_t *lut3, uint32_t group,
 																										unsigned lane) {
 	constexpr int bpw = WS::kBlocks;
@@ -1190,7 +1192,7 @@ __device__ __forceinline__ void window_group_single(const AmdParams &p, WS &ws, 
 	}
 	__syncwarp();
 	// shake_subset (:709-805): ep_shaker_2_d on the quantiser's indices and, where ep_shaker_d won, again on its indices
-	window_phase(T, ws, lut2, lut3, wtasks, sp.dim, wtype, lane);
+	window_phase<CLOGS>(T, ws, lut2, lut3, wtasks, sp.dim, wtype, lane);
 	AMD_T(3);
 	if (cube) {
 		if ((int) lane < wtasks) {
@@ -1199,7 +1201,7 @@ __device__ __forceinline__ void window_group_single(const AmdParams &p, WS &ws, 
 			t.w_index = t.best_idx;
 		}
 		__syncwarp();
-		window_phase(T, ws, lut2, lut3, wtasks, sp.dim, wtype, lane);
+		window_phase<CLOGS>(T, ws, lut2, lut3, wtasks, sp.dim, wtype, lane);
 		AMD_T(4);
 	}
 	ShakeOut o;
@@ -1245,13 +1247,13 @@ __device__ __forceinline__ void window_group_single(const AmdParams &p, WS &ws, 
 
 // 8 warps per CTA: 2 CTAs (16 warps) fit the 227 KB of shared memory next to one copy of the ramp tables each
 constexpr int kWindowWarps = 8, kWindowCtasPerSm = 2;
-template <typename WS> __global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
+template <typename WS, int CLOGS> __global__ void __launch_bounds__(kWindowWarps * 32, kWindowCtasPerSm) amd_window_kernel(const AmdParams p) {
 	constexpr bool kDual = std::is_same<WS, WindowScratchDual>::value;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WS *scratch = reinterpret_cast<WS *>(smem_raw);
 	__shared__ uint32_t lut2[RampLutShape<2>::kWords], lut3[RampLutShape<3>::kWords];
-	ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWindowWarps * 32);
-	ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWindowWarps * 32);
+	if (CLOGS & 4) ramp_lut_fill<2>(lut2, (int) threadIdx.x, kWindowWarps * 32);
+	if (CLOGS & 8) ramp_lut_fill<3>(lut3, (int) threadIdx.x, kWindowWarps * 32);
 	__syncthreads();
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
 	WS &ws = scratch[warp];
@@ -1262,8 +1264,8 @@ template <typename WS> __global__ void __launch_bounds__(kWindowWarps * 32, kWin
 	for (;;) {
 		const uint32_t group = fetch_block(p.next_block, lane);
 		if (group >= groups) break;
-		if constexpr (kDual) window_group_dual(p, ws, T, lut2, lut3, group, lane);
-		else window_group_single(p, ws, T, lut2, lut3, group, lane);
+		if constexpr (kDual) window_group_dual<CLOGS>(p, ws, T, lut2, lut3, group, lane);
+		else window_group_single<CLOGS>(p, ws, T, lut2, lut3, group, lane);
 	}
 }
 // (2 CTAs of 8 warps and their tables fit the shared memory of an SM)
@@ -1580,6 +1582,27 @@ extern "C" __attribute__((visibility("default"))) int b200ic_profile_read(double
 	return n;
 }
 
+// The window kernel of a mode: sets its shared-memory attribute (p == nullptr) or launches it
+namespace {
+template <typename WS, int CLOGS> cudaError_t window_kernel_do(const AmdParams *p, unsigned grid, cudaStream_t stream) {
+	if (!p) return cudaFuncSetAttribute(amd_window_kernel<WS, CLOGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WS)));
+	amd_window_kernel<WS, CLOGS><<<grid, kWindowWarps * 32, kWindowWarps * sizeof(WS), stream>>>(*p);
+	return cudaSuccess;
+}
+cudaError_t window_kernel_launch(int mode, const AmdParams *p, unsigned grid, cudaStream_t stream) {
+	switch (mode) {
+	case 0: return window_kernel_do<WindowScratch1, mode_clogs(0)>(p, grid, stream);
+	case 1: return window_kernel_do<WindowScratch2, mode_clogs(1)>(p, grid, stream);
+	case 2: return window_kernel_do<WindowScratch1, mode_clogs(2)>(p, grid, stream);
+	case 3: return window_kernel_do<WindowScratch2, mode_clogs(3)>(p, grid, stream);
+	case 4: return window_kernel_do<WindowScratchDual, mode_clogs(4)>(p, grid, stream);
+	case 5: return window_kernel_do<WindowScratchDual, mode_clogs(5)>(p, grid, stream);
+	case 7: return window_kernel_do<WindowScratch1, mode_clogs(7)>(p, grid, stream);
+	default: return cudaErrorInvalidValue;
+	}
+}
+} // namespace
+
 cudaError_t init_bc7amd_tables() {
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
@@ -1642,12 +1665,11 @@ cudaError_t init_bc7amd_tables() {
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(amd_quant_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(DualQuantScratch)));
 	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel<WindowScratch1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch1)));
-	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel<WindowScratch2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratch2)));
-	if (e != cudaSuccess) return e;
-	e = cudaFuncSetAttribute(amd_window_kernel<WindowScratchDual>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWindowWarps * sizeof(WindowScratchDual)));
-	if (e != cudaSuccess) return e;
+	for (int mode = 0; mode < 8; mode++) {
+		if (mode == 6) continue;
+		e = window_kernel_launch(mode, nullptr, 0, nullptr);
+		if (e != cudaSuccess) return e;
+	}
 	e = cudaFuncSetAttribute(bc7amd_float_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kWarps * sizeof(FloatScratch)));
 	if (e != cudaSuccess) return e;
 	g_sp_table_host[dev] = d;
@@ -1739,14 +1761,17 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 				if (mode != 7) {
 					ProfScope ps(stream, mode, 1);
 					p.next_block = counter++;
-					amd_cube_kernel<<<cube_grid, kWarps * 32, 0, stream>>>(p);
+					// (second-pass pruning pays where an item has 256 corners: mode 0; mode 2 with 64 measured 2x slower)
+					if (mode == 0) amd_cube_kernel<mode_clogs(0), true><<<cube_grid, kWarps * 32, 0, stream>>>(p);
+					else if (mode == 1) amd_cube_kernel<mode_clogs(1), false><<<cube_grid, kWarps * 32, 0, stream>>>(p);
+					else if (mode == 4) amd_cube_kernel<mode_clogs(4), false><<<cube_grid, kWarps * 32, 0, stream>>>(p);
+					else amd_cube_kernel<4, false><<<cube_grid, kWarps * 32, 0, stream>>>(p);
 				}
 				{
 					ProfScope ps(stream, mode, 2);
 					p.next_block = counter++;
-					if (mode == 4 || mode == 5) amd_window_kernel<WindowScratchDual><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratchDual), stream>>>(p);
-					else if (mode == 1 || mode == 3) amd_window_kernel<WindowScratch2><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch2), stream>>>(p);
-					else amd_window_kernel<WindowScratch1><<<window_grid, kWindowWarps * 32, kWindowWarps * sizeof(WindowScratch1), stream>>>(p);
+					e = window_kernel_launch(mode, &p, window_grid, stream);
+					if (e != cudaSuccess) break;
 				}
 				launches += mode != 7 ? 3 : 2;
 			}

@@ -608,13 +608,39 @@ template <int CLOG> A7_HD uint32_t cube_tab_word(const uint32_t ep[6], int bcc, 
 	const int e1 = (int) ((ep[k] >> (16 * odd + 8 * (x & 1))) & 255u), e2 = (int) ((ep[3 + k] >> (16 * (odd ^ flip) + 8 * (x >> 1))) & 255u);
 	return ramp_word<CLOG>(e1, e2, 4 * hf);
 }
+// sum over the texels of the smallest squared distance to the palette.  d: 16 words, 16-byte aligned (shared memory on the
+// GPU: every lane of the warp reads the same address).  The texel loop is ROLLED, four texels per trip: with the 16 texels
+// of the dual-index modes unrolled, a corner was 340 instructions of straight-line code run twice per work item, and the
+// cube kernel stalled on instruction fetch more than on anything else (profiles/r2_notes.md).
+template <int CLOG> A7_HD uint32_t palette_error_u8(const uint32_t *pal, const uint32_t *d, int n) {
+	constexpr int C = 1 << CLOG;
+	uint32_t err = 0;
+#pragma unroll 1
+	for (int t0 = 0; t0 < n; t0 += 4) {
+#if defined(__CUDA_ARCH__)
+		const uint4 dv = *reinterpret_cast<const uint4 *>(d + t0);
+		const uint32_t dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#else
+		const uint32_t dd[4] = {d[t0], d[t0 + 1], d[t0 + 2], d[t0 + 3]};
+#endif
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (t0 + k >= n) break; // n is warp-uniform on the GPU
+			uint32_t m = sq_dist4(pal[0], dd[k]);
+#pragma unroll
+			for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], dd[k]));
+			err += m;
+		}
+	}
+	return err;
+}
 // Corner -> lane map, nlb = log2(lattices): lane bits (LSB first) = lattice (nlb bits), z (2), then
 //   nlb 2: y bit 0          ; the lane walks y bit 1 (outer) and x (inner) : 8 corners
 //   nlb 1: y                ; the lane walks x                             : 4 corners
 //   nlb 0: y, x bit 0       ; the lane walks x bit 1                       : 2 corners
 // key = err << 8 | lattice << 6 | gray position (gray_position is linear over GF(2): one XOR per corner)
 template <int CLOG>
-A7_HD void cube_lane_corners(const uint64_t *tab, const uint32_t (&d)[16], int n, int nlb, unsigned lane, uint32_t &best_key, uint32_t &best_xy) {
+A7_HD void cube_lane_corners(const uint64_t *tab, const uint32_t *d, int n, int nlb, unsigned lane, uint32_t &best_key, uint32_t &best_xy) {
 	constexpr int C = 1 << CLOG;
 	const int l = (int) lane & ((1 << nlb) - 1), rest = (int) lane >> nlb;
 	const int z = rest & 3;
@@ -640,15 +666,7 @@ A7_HD void cube_lane_corners(const uint64_t *tab, const uint32_t (&d)[16], int n
 			uint32_t pal[C];
 #pragma unroll
 			for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<0>(pzy[c], tx, c);
-			uint32_t err = 0;
-#pragma unroll
-			for (int t = 0; t < 16; t++) {
-				if (t >= n) break; // n is warp-uniform on the GPU: one branch per texel, none after the last
-				uint32_t m = sq_dist4(pal[0], d[t]);
-#pragma unroll
-				for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], d[t]));
-				err += m;
-			}
+			const uint32_t err = palette_error_u8<CLOG>(pal, d, n);
 			const uint32_t key = (err << 8) | (gzy ^ (uint32_t) gray_position(x));
 			if (key < best_key) {
 				best_key = key;
@@ -769,19 +787,7 @@ template <int CLOG> A7_HD void cube_cid_palette(const uint64_t *tab, int cid, ui
 	for (int c = 0; c < C; c++) pal[c] = put_ramp_byte<2>(put_ramp_byte<1>(put_ramp_byte<0>(0u, tx, c), ty, c), tz, c);
 }
 A7_HD uint32_t cube_cid_key(uint32_t err, int cid) { return (err << 8) | (uint32_t) (cid & 0xc0) | (uint32_t) gray_position(cid & 63); }
-template <int CLOG> A7_HD uint32_t cube_corner_error_u8(const uint32_t *pal, const uint32_t (&d)[16], int n) {
-	constexpr int C = 1 << CLOG;
-	uint32_t err = 0;
-#pragma unroll
-	for (int t = 0; t < 16; t++) {
-		if (t >= n) break;
-		uint32_t m = sq_dist4(pal[0], d[t]);
-#pragma unroll
-		for (int c = 1; c < C; c++) m = umin32(m, sq_dist4(pal[c], d[t]));
-		err += m;
-	}
-	return err;
-}
+template <int CLOG> A7_HD uint32_t cube_corner_error_u8(const uint32_t *pal, const uint32_t *d, int n) { return palette_error_u8<CLOG>(pal, d, n); }
 
 // ---- ramps from a difference table ---------------------------------------------------------------------------------
 // ramp entry c between expanded endpoints e1, e2 = floor((2 D e1 + D + 2 c (e2 - e1)) / (2 D)) = e1 + off(e2 - e1, c), and

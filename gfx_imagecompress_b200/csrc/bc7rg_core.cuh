@@ -741,6 +741,7 @@ B7_HD void encode_block(const uint32_t px[16], const Params &P, uint64_t out[2])
 	r.lo[1] = r.hi[1] = 0;
 	r.pbit[1][0] = r.pbit[1][1] = 0;
 	Best b6;
+	bool mode1 = false;
 	if (alpha) {
 		compress_cell<6, true>(cell, P, b6);
 	} else {
@@ -750,40 +751,45 @@ B7_HD void encode_block(const uint32_t px[16], const Params &P, uint64_t out[2])
 			const uint32_t mask = kPart2[part];
 			Best bs[2];
 			uint64_t trial = 0;
+#pragma unroll 1
 			for (int k = 0; k < 2; k++) {
 				Cell sub;
 				sub.n = 0;
+#pragma unroll 1
 				for (int i = 0; i < 16; i++)
 					if (((mask >> i) & 1u) == (uint32_t) k) sub.px[sub.n++] = px[i];
 				trial += compress_cell<1, false>(sub, P, bs[k]);
 				if (trial > err6) break;
 			}
 			if (trial < err6) {
+				mode1 = true;
 				r.mode = 1;
 				r.partition = part;
 				uint64_t sel = 0;
 				int cnt[2] = {0, 0};
+#pragma unroll 1
 				for (int i = 0; i < 16; i++) {
 					const int k = (int) ((mask >> i) & 1u);
 					sel |= sel_put(sel_get(bs[k].sel, cnt[k]++), i);
 				}
 				r.sel = sel;
+#pragma unroll
 				for (int k = 0; k < 2; k++) {
 					r.lo[k] = bs[k].lo;
 					r.hi[k] = bs[k].hi;
 					r.pbit[k][0] = bs[k].pbit[0];
 					r.pbit[k][1] = 0;
 				}
-				pack_block(r, out);
-				return;
 			}
 		}
 	}
-	r.sel = b6.sel;
-	r.lo[0] = b6.lo;
-	r.hi[0] = b6.hi;
-	r.pbit[0][0] = b6.pbit[0];
-	r.pbit[0][1] = b6.pbit[1];
+	if (!mode1) {
+		r.sel = b6.sel;
+		r.lo[0] = b6.lo;
+		r.hi[0] = b6.hi;
+		r.pbit[0][0] = b6.pbit[0];
+		r.pbit[0][1] = b6.pbit[1];
+	}
 	pack_block(r, out);
 }
 
