@@ -503,11 +503,25 @@ template <int DIM, class IO> A7_HD real quantise_points(const IO &io, int n, int
 				// running k (:1977-1984). The boundaries are non-decreasing in k (t >= 0), so for sorted input the
 				// running k of an element equals the NUMBER of boundaries it exceeds: no sort, no dependent loop.
 				b = 0;
+				if (clusters <= 8) { // the (up to 7) boundaries in registers, one pass over the projections
+					real bound[7];
+#pragma unroll
+					for (int c = 0; c < 7; c++) bound[c] = c < clusters - 1 ? ((real) c + 0.5 - s) * t : 0;
 #pragma unroll 1
-				for (int c = 0; c < clusters - 1; c++) {
-					const real bound = ((real) c + 0.5 - s) * t;
+					for (int j = 0; j < n; j++) {
+						const real pj = io.get_proj(j);
+						int cnt = 0;
+#pragma unroll
+						for (int c = 0; c < 7; c++) cnt += (c < clusters - 1 && pj > bound[c]) ? 1 : 0;
+						b |= (uint64_t) cnt << (4 * j);
+					}
+				} else {
 #pragma unroll 1
-					for (int j = 0; j < n; j++) b += (uint64_t) (io.get_proj(j) > bound ? 1 : 0) << (4 * j);
+					for (int c = 0; c < clusters - 1; c++) {
+						const real bound = ((real) c + 0.5 - s) * t;
+#pragma unroll 1
+						for (int j = 0; j < n; j++) b += (uint64_t) (io.get_proj(j) > bound ? 1 : 0) << (4 * j);
+					}
 				}
 				slot = memo_next;
 				memo_next = (memo_next + 1) & 3;
