@@ -395,11 +395,25 @@ H6_HDN uint64_t quantise_points_f(const QuantIOF &io, int n, int clusters, float
 				// boundaries (k + 0.5 - s) * t are evaluated in double by the reference's mixed expression (:1549);
 				// they are non-decreasing in k, so the running-k walk over sorted projections == counting
 				b = 0;
+				if (clusters <= 8) { // (two-region fits) the boundaries in registers, one pass over the projections
+					double bound[7];
+#pragma unroll
+					for (int c = 0; c < 7; c++) bound[c] = ((double) c + 0.5 - (double) s) * (double) t;
 #pragma unroll 1
-				for (int c = 0; c < clusters - 1; c++) {
-					const double bound = ((double) c + 0.5 - (double) s) * (double) t;
+					for (int j = 0; j < n; j++) {
+						const double pj = (double) io.proj[j * st];
+						int cnt = 0;
+#pragma unroll
+						for (int c = 0; c < 7; c++) cnt += (c < clusters - 1 && pj > bound[c]) ? 1 : 0;
+						b |= (uint64_t) cnt << (4 * j);
+					}
+				} else {
 #pragma unroll 1
-					for (int j = 0; j < n; j++) b += (uint64_t) ((double) io.proj[j * st] > bound ? 1 : 0) << (4 * j);
+					for (int c = 0; c < clusters - 1; c++) {
+						const double bound = ((double) c + 0.5 - (double) s) * (double) t;
+#pragma unroll 1
+						for (int j = 0; j < n; j++) b += (uint64_t) ((double) io.proj[j * st] > bound ? 1 : 0) << (4 * j);
+					}
 				}
 				slot = memo_next;
 				memo_next = (memo_next + 1) & 3;
