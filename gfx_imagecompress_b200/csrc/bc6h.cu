@@ -3,13 +3,15 @@
 // Replaces the image loop of reference src/amd_bc6h_compressor.cpp:10-58 (gather via block_utils.cpp:7-41) and
 // BC6HBlockEncoder::CompressBlock (src/amd_bc6h_body.cpp:1521-1652); the search is bc6h_core.cuh.
 //
-// Mapping: one warp per group of kGroup = 4 consecutive 4x4 blocks, candidates -> lanes.
+// Mapping: one warp per group of kGroup = 8 consecutive 4x4 blocks, candidates -> lanes.
 //   shape phase : per block, lane s fits two-region shape s (partition, two optQuantAnD problems, end points, palette
 //                 error); lexicographic (error, shape) arg-min by warp shuffles = the reference's first strict minimum
-//   gate phase  : the one-region fit, whose error only gates the scan in the reference, for the group's 4 blocks on
-//                 lanes 0..3 at once (one lane per block would otherwise idle the warp for a third of its time)
-//   mode phase  : the 4 x 10 (block, two-region mode) trials spread over the lanes; lanes 0..3 then replay the
-//                 reference's in-order scan over their block's results and pack it
+//   gate phase  : the one-region fit, whose error only gates the scan in the reference, for the group's 8 blocks on
+//                 lanes 0..7 at once (one lane per block would otherwise idle the warp for a third of its time)
+//   mode phase  : the 8 x 10 (block, two-region mode) trials spread over the lanes (2.5 full rounds); lanes 0..7 then
+//                 replay the reference's in-order scan over their block's results and pack it
+// The per-block scratch is ~1.1 KB (trial results packed: 16-bit endpoint fields, 4-bit indices), so that a group of 8
+// and 4 CTAs per SM fit the shared memory.
 // The quantiser reads the block channel-major from shared memory and keeps its work arrays lane-strided in shared
 // memory; palettes live in registers: no local-memory arrays in the shape phase.
 // FP32 in the reference's operation order, --fmad=false: blocks are bit-identical to the reference on every test
@@ -25,19 +27,24 @@ namespace {
 using namespace bc6;
 
 constexpr int kWarps = 4;
-constexpr int kGroup = 4;
+constexpr int kGroup = 8;
 
+struct TrialResults { // of the 10 two-region modes of one block (index 0 unused)
+	float err[11];
+	uint8_t fits[11], second[11];
+	uint16_t q[11][2][2][3]; // transformed / masked endpoint fields (<= 16 bits)
+	uint64_t idx[11][2];     // 4 bits per entry
+};
 struct BlockScratch {
-	float in[64];
 	float din[16][4];
 	float pxc[48];
 	ShapeFit fit, fit31; // best two-region shape / shape 31 (what the reference encodes when the one-region fit wins)
 	float emin;
 	int who, shape;
-	float err[11];
-	int fits[11], second[11];
-	int q[11][2][2][3];
-	int idx[11][2][kMaxEntries];
+	union {
+		float in[64];    // the gathered block (until prepare_block)
+		TrialResults tr; // mode phase
+	};
 };
 struct WarpScratch {
 	BlockScratch b[kGroup];
@@ -51,7 +58,8 @@ struct Bc6Params {
 	int is_signed;
 };
 
-__global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
+static_assert(kWarps * sizeof(WarpScratch) <= 233472 / 4 - 1024, "4 CTAs per SM");
+__global__ void __launch_bounds__(kWarps * 32, 4) bc6h_kernel(const Bc6Params p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw);
 	const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -116,10 +124,24 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 		float err = FLT_MAX;
 		bool second = false;
 		const ShapeFit fit = B.fit;
-		const bool fits = try_mode(B.din, fit, B.shape, mode, err, second, B.q[mode], B.idx[mode], sgn);
-		B.err[mode] = err;
-		B.fits[mode] = fits ? 1 : 0;
-		B.second[mode] = second ? 1 : 0;
+		int q[2][2][3], idx[2][kMaxEntries];
+		const bool fits = try_mode(B.din, fit, B.shape, mode, err, second, q, idx, sgn);
+		B.tr.err[mode] = err;
+		B.tr.fits[mode] = fits ? 1 : 0;
+		B.tr.second[mode] = second ? 1 : 0;
+		if (fits) {
+#pragma unroll 1
+			for (int s = 0; s < 2; s++) {
+				uint64_t packed = 0;
+#pragma unroll 1
+				for (int k = 0; k < kMaxEntries; k++) packed |= (uint64_t) (idx[s][k] & 15) << (4 * k);
+				B.tr.idx[mode][s] = packed;
+#pragma unroll 1
+				for (int ee = 0; ee < 2; ee++)
+#pragma unroll 1
+					for (int c = 0; c < 3; c++) B.tr.q[mode][s][ee][c] = (uint16_t) q[s][ee][c];
+			}
+		}
 	}
 	__syncwarp();
 	if ((int) lane < nb) {
@@ -127,9 +149,9 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 		bool fits[11], second[11];
 		float err[11];
 		for (int m = 1; m <= 10; m++) {
-			fits[m] = B.fits[m] != 0;
-			second[m] = B.second[m] != 0;
-			err[m] = B.err[m];
+			fits[m] = B.tr.fits[m] != 0;
+			second[m] = B.tr.second[m] != 0;
+			err[m] = B.tr.err[m];
 		}
 		Encoded E;
 		E.mode = pick_mode(fits, err, second);
@@ -137,9 +159,9 @@ __global__ void __launch_bounds__(kWarps * 32) bc6h_kernel(const Bc6Params p) {
 		if (E.mode) {
 			for (int s = 0; s < 2; s++)
 				for (int ee = 0; ee < 2; ee++)
-					for (int c = 0; c < 3; c++) E.q[s][ee][c] = B.q[E.mode][s][ee][c];
+					for (int c = 0; c < 3; c++) E.q[s][ee][c] = (int) B.tr.q[E.mode][s][ee][c];
 			for (int s = 0; s < 2; s++)
-				for (int k = 0; k < kMaxEntries; k++) E.idx[s][k] = B.idx[E.mode][s][k];
+				for (int k = 0; k < kMaxEntries; k++) E.idx[s][k] = (int) ((B.tr.idx[E.mode][s] >> (4 * k)) & 15u);
 		}
 		uint64_t out[2];
 		pack_block(E, out);

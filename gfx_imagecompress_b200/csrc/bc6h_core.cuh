@@ -395,24 +395,20 @@ H6_HDN uint64_t quantise_points_f(const QuantIOF &io, int n, int clusters, float
 				// boundaries (k + 0.5 - s) * t are evaluated in double by the reference's mixed expression (:1549);
 				// they are non-decreasing in k, so the running-k walk over sorted projections == counting
 				b = 0;
-				if (clusters <= 8) { // (two-region fits) the boundaries in registers, one pass over the projections
+				// the boundaries in registers, seven at a time (two-region fits have 7, the one-region fit 15): one pass over
+				// the projections per chunk instead of one per boundary
+#pragma unroll 1
+				for (int c0 = 0; c0 < clusters - 1; c0 += 7) {
 					double bound[7];
 #pragma unroll
-					for (int c = 0; c < 7; c++) bound[c] = ((double) c + 0.5 - (double) s) * (double) t;
+					for (int c = 0; c < 7; c++) bound[c] = ((double) (c0 + c) + 0.5 - (double) s) * (double) t;
 #pragma unroll 1
 					for (int j = 0; j < n; j++) {
 						const double pj = (double) io.proj[j * st];
 						int cnt = 0;
 #pragma unroll
-						for (int c = 0; c < 7; c++) cnt += (c < clusters - 1 && pj > bound[c]) ? 1 : 0;
-						b |= (uint64_t) cnt << (4 * j);
-					}
-				} else {
-#pragma unroll 1
-					for (int c = 0; c < clusters - 1; c++) {
-						const double bound = ((double) c + 0.5 - (double) s) * (double) t;
-#pragma unroll 1
-						for (int j = 0; j < n; j++) b += (uint64_t) ((double) io.proj[j * st] > bound ? 1 : 0) << (4 * j);
+						for (int c = 0; c < 7; c++) cnt += (c0 + c < clusters - 1 && pj > bound[c]) ? 1 : 0;
+						b += (uint64_t) cnt << (4 * j);
 					}
 				}
 				slot = memo_next;
@@ -576,28 +572,35 @@ template <int REGIONS> H6_HD float fit_shape_t(const float *pxc, int shape, Shap
 	F.idx[0] = F.idx[1] = 0;
 	F.count[0] = F.count[1] = 0;
 #pragma unroll
-	for (int s = 0; s < 2; s++) {
-		if (s < REGIONS) {
-			QuantIOF io;
-			io.px = pxc;
-			io.proj = proj;
-			io.dev = dev;
-			io.stride = stride;
-			int n;
-			io.texels = texels_of_mask(REGIONS == 1 ? 0xffffu : (s ? mask : (~mask & 0xffffu)), n);
-			F.count[s] = n;
-			float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
-			F.idx[s] = quantise_points_f(io, n, REGIONS == 2 ? 8 : 16, lo, hi);
-			// clampF16Max (:506-528)
-			const float floor_v = is_signed ? -31743.f : 0.f;
+	for (int c = 0; c < 3; c++) F.ep[1][0][c] = F.ep[1][1][c] = 0.f;
+	// The LARGER region first: the 32 lanes of a warp fit the 32 shapes of a block, and a quantiser call costs what its
+	// largest region costs -- calls of 8 .. 15 and then 1 .. 8 texels instead of 1 .. 15 twice.  (The two fits are independent.)
+	int big = 0;
+	if (REGIONS == 2) {
+		int n1 = 0;
 #pragma unroll
-			for (int c = 0; c < 3; c++) {
-				F.ep[s][0][c] = lo[c] < floor_v ? floor_v : (lo[c] > 31743.f ? 31743.f : lo[c]);
-				F.ep[s][1][c] = hi[c] < floor_v ? floor_v : (hi[c] > 31743.f ? 31743.f : hi[c]);
-			}
-		} else {
+		for (int i = 0; i < 16; i++) n1 += (int) ((mask >> i) & 1u);
+		big = n1 > 8 ? 1 : 0;
+	}
+#pragma unroll 1
+	for (int k = 0; k < REGIONS; k++) {
+		const int s = k ^ big;
+		QuantIOF io;
+		io.px = pxc;
+		io.proj = proj;
+		io.dev = dev;
+		io.stride = stride;
+		int n;
+		io.texels = texels_of_mask(REGIONS == 1 ? 0xffffu : (s ? mask : (~mask & 0xffffu)), n);
+		F.count[s] = n;
+		float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+		F.idx[s] = quantise_points_f(io, n, REGIONS == 2 ? 8 : 16, lo, hi);
+		// clampF16Max (:506-528)
+		const float floor_v = is_signed ? -31743.f : 0.f;
 #pragma unroll
-			for (int c = 0; c < 3; c++) F.ep[s][0][c] = F.ep[s][1][c] = 0.f;
+		for (int c = 0; c < 3; c++) {
+			F.ep[s][0][c] = lo[c] < floor_v ? floor_v : (lo[c] > 31743.f ? 31743.f : lo[c]);
+			F.ep[s][1][c] = hi[c] < floor_v ? floor_v : (hi[c] > 31743.f ? 31743.f : hi[c]);
 		}
 	}
 	return shape_error_direct<REGIONS>(pxc, F.ep, mask);
