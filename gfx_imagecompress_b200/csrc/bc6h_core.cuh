@@ -364,8 +364,10 @@ H6_HDN uint64_t quantise_points_f(const QuantIOF &io, int n, int clusters, float
 	uint32_t gvalid = 0;
 	int memo_n = 0, memo_next = 0;
 	constexpr int kHist = 8;
-	uint64_t hist[kHist];
+	uint64_t hist[kHist]; // shift register (static indices: registers): hist[k] = the state k + 1 iterations ago
 	int hist_try[kHist];
+#pragma unroll
+	for (int k = 0; k < kHist; k++) { hist[k] = 0; hist_try[k] = 0; }
 	uint64_t first = 0;
 	int try_two = 50;
 	float s, t;
@@ -445,20 +447,24 @@ H6_HDN uint64_t quantise_points_f(const QuantIOF &io, int n, int clusters, float
 		}
 		if (it >= 2) {
 			int period = 0;
-#pragma unroll 1
-			for (int pd = 1; pd <= kHist && pd <= it - 1; pd++) {
-				const int h = (it + 1 - pd) & (kHist - 1);
-				if (hist[h] == cur && (hist_try[h] == try_two || hist_try[h] < 0)) { period = pd; break; }
-			}
+#pragma unroll
+			for (int pd = 1; pd <= kHist; pd++)
+				if (!period && pd <= it - 1 && hist[pd - 1] == cur && (hist_try[pd - 1] == try_two || hist_try[pd - 1] < 0)) period = pd;
 			if (period) {
-				const int r = (kQuantMaxTry - 1 - it) % period;
-				cur = hist[(it + 1 - period + r) & (kHist - 1)];
+				const int r = (kQuantMaxTry - 1 - it) % period; // iterations still to run, modulo the period
+				const int back = period - r - 1;                // the final state, as an age in the shift register
+				uint64_t v = hist[0];
+#pragma unroll
+				for (int k = 1; k < kHist; k++) v = back == k ? hist[k] : v;
+				cur = v;
 				H6_STATS_IT(kQuantMaxTry + 1);
 				break;
 			}
 		}
-		hist[(it + 1) & (kHist - 1)] = cur;
-		hist_try[(it + 1) & (kHist - 1)] = try_two;
+#pragma unroll
+		for (int k = kHist - 1; k > 0; k--) { hist[k] = hist[k - 1]; hist_try[k] = hist_try[k - 1]; }
+		hist[0] = cur;
+		hist_try[0] = try_two;
 		if (it == kQuantMaxTry - 1) { H6_STATS_IT(kQuantMaxTry); }
 	}
 	// the ramp points (:1578-1600) and, of those, the ones with the smallest / largest channel sum (GetEndPoints)
