@@ -725,11 +725,51 @@ H6_HDN bool try_mode(const float din[16][4], const ShapeFit &F, int shape, int m
 		for (int e = 0; e < 2; e++)
 #pragma unroll 1
 			for (int c = 0; c < 3; c++) un[s][e][c] = (float) ((unquantize_u(udec[s][e][c], md.nbits) * 31) >> 6);
-	float pal[2][16][3];
-	build_palette(un, 2, pal);
+	// The palettes of both regions in REGISTERS (every index static) and one pass over the texels for ReIndexShapef
+	// (:838-902: first strict minimum) and CalcShapeError (:783-836: the early-exit scan, as a flag): with the palette as a
+	// local-memory array the two scans were 33 % of the kernel's stall samples for 10 % of its instructions.
+	float pal[2][8][3];
+#pragma unroll
+	for (int r = 0; r < 2; r++)
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+#pragma unroll
+			for (int c = 0; c < 3; c++) pal[r][j][c] = lerp_weighted(un[r][0][c], un[r][1][c], j, 7);
 	const uint32_t mask = kShape[shape];
-	if (is_signed) { // no re-indexing, no second quantisation for signed sources (:1436, :1456)
-		err = shape_error(din, pal, 2, mask);
+	int pos[2] = {0, 0};
+	float total = 0.f;
+#pragma unroll 1
+	for (int i = 0; i < 16; i++) {
+		const int s = (int) ((mask >> i) & 1u);
+		const float d0 = din[i][0], d1 = din[i][1], d2 = din[i][2];
+		float e[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const float p0 = s ? pal[1][j][0] : pal[0][j][0], p1 = s ? pal[1][j][1] : pal[0][j][1], p2 = s ? pal[1][j][2] : pal[0][j][2];
+			e[j] = fabsf(d0 - p0) + fabsf(d1 - p1) + fabsf(d2 - p2);
+		}
+		if (!is_signed) { // no re-indexing for signed sources (:1436)
+			float best = FLT_MAX;
+			int bi = 0;
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				if (e[j] < best) { best = e[j]; bi = j; }
+			idx[s][pos[s]++] = bi;
+		}
+		float sb = e[0];
+		bool go = sb > 0;
+#pragma unroll
+		for (int j = 1; j < 8; j++) {
+			if (go) {
+				if (e[j] <= sb) sb = e[j];
+				else go = false;
+			}
+			go = go && sb > 0;
+		}
+		total += sb;
+	}
+	err = total;
+	if (is_signed) { // ... and no second quantisation (:1456)
 		second_fit = true;
 #pragma unroll 1
 		for (int s = 0; s < 2; s++) {
@@ -742,21 +782,6 @@ H6_HDN bool try_mode(const float din[16][4], const ShapeFit &F, int shape, int m
 		}
 		return true;
 	}
-	// ReIndexShapef (:838-902)
-	int pos[2] = {0, 0};
-#pragma unroll 1
-	for (int i = 0; i < 16; i++) {
-		const int s = (int) ((mask >> i) & 1u);
-		float best = FLT_MAX;
-		int bi = 0;
-#pragma unroll 1
-		for (int j = 0; j < 8; j++) {
-			const float e = fabsf(din[i][0] - pal[s][j][0]) + fabsf(din[i][1] - pal[s][j][1]) + fabsf(din[i][2] - pal[s][j][2]);
-			if (e < best) { best = e; bi = j; }
-		}
-		idx[s][pos[s]++] = bi;
-	}
-	err = shape_error(din, pal, 2, mask);
 	// what the reference does when this mode beats the running best (:1453-1459)
 	quantise_endpoints(un, f16, md.nbits, false);
 	swap_indices(f16, idx, F.count, shape);
