@@ -401,12 +401,20 @@ H6_HDN uint64_t quantise_points_f(const QuantIOF &io, int n, int clusters, float
 				// the projections per chunk instead of one per boundary
 #pragma unroll 1
 				for (int c0 = 0; c0 < clusters - 1; c0 += 7) {
+#if defined(__CUDA_ARCH__)
+					// p > bound for a float p and a double bound  <=>  p > the bound rounded DOWN to float (the largest float not
+					// above it): the comparisons run in FP32
+					float bound[7];
+#pragma unroll
+					for (int c = 0; c < 7; c++) bound[c] = __double2float_rd(((double) (c0 + c) + 0.5 - (double) s) * (double) t);
+#else
 					double bound[7];
 #pragma unroll
 					for (int c = 0; c < 7; c++) bound[c] = ((double) (c0 + c) + 0.5 - (double) s) * (double) t;
+#endif
 #pragma unroll 1
 					for (int j = 0; j < n; j++) {
-						const double pj = (double) io.proj[j * st];
+						const float pj = io.proj[j * st];
 						int cnt = 0;
 #pragma unroll
 						for (int c = 0; c < 7; c++) cnt += (c0 + c < clusters - 1 && pj > bound[c]) ? 1 : 0;
