@@ -557,6 +557,22 @@ A7_HDN void cube_item_u8(const uint32_t *d, int n, uint64_t collapsed, int q, in
 #endif
 }
 
+// ep_find_floor (:351-367) in closed form.  The reference bisects for the largest lattice index j >= 1 with
+// expand(code(j)) <= v, code(j) = (j << use_par) + odd, and answers j = 0 when there is none.  v >= x <=> floor(v) >= x for
+// integer x, expand_bits is increasing and expand(x) >= x << (8 - bits), so the largest code X with expand(X) <= floor(v) is
+// floor(v) >> (8 - bits) or one less, and j = (X - odd) >> use_par (0 when X < odd).  bits >= 4.  (The bisection was as
+// expensive as the window search it feeds: ~50 instructions, two calls per (item, channel, parity combination).)
+A7_HD int endpoint_floor_int(real v, int bits, int use_par, int odd) {
+	const int iv = (v >= 0) ? ((v >= 255.) ? 255 : (int) v) : -1; // NaN -> -1
+	odd = use_par ? odd : 0;
+	int X = -1;
+	if (iv >= 0) {
+		const int xh = iv >> (8 - bits);
+		X = expand_bits(bits, xh) <= iv ? xh : xh - 1;
+	}
+	const int j = X >= odd ? (X - odd) >> use_par : 0;
+	return (j << use_par) + odd;
+}
 // ---- lane = corner form of the cube walk (the CUDA cube kernel of bc7amd.cu) ----------------------------------------
 // One work item = one (q, p) re-indexing of one task.  Its set-up runs on one lane per item (32 items at a time); the
 // ramp tables of all its lattices are then built by the 32 lanes together, and the (lattices x 64) corners are dealt
@@ -580,7 +596,7 @@ template <int CLOG> A7_HD void cube_item_setup_u8(const uint32_t *d, int n, uint
 			uint32_t w = 0;
 #pragma unroll 1
 			for (int par = 0; par <= use_par; par++) {
-				const int f = endpoint_floor(epa[e][k], bits, use_par, par);
+				const int f = endpoint_floor_int(epa[e][k], bits, use_par, par);
 				const int up = f + ((top - f < reach ? top - f : reach) & ~use_par);
 				w |= ((uint32_t) expand_bits(bits, f) | ((uint32_t) expand_bits(bits, up) << 8)) << (16 * par);
 			}
@@ -1015,17 +1031,6 @@ A7_HDN uint32_t window_item_u8(const uint32_t *d, int n, uint64_t collapsed, int
 // byte permute (4 texels per PRMT, selectors built once per item), and |r - d| / its square are 4-wide byte
 // instructions against the channel plane of the data -- 3 instructions per 4 texels and candidate.
 // sum_m (r[cidx[m]] - d[m])^2 is the same integer the cluster form computes, so the search is identical.
-A7_HD int endpoint_floor_int(real v, int bits, int use_par, int odd) { // ep_find_floor with the comparisons done on floor(v)
-	const int iv = (v >= 0) ? ((v >= 256.) ? 256 : (int) v) : -1;        // v >= x  <=>  floor(v) >= x for integer x; NaN -> -1
-	int i1 = 0, i2 = 1 << (bits - use_par);
-	odd = use_par ? odd : 0;
-	while (i2 - i1 > 1) {
-		const int j = (i1 + i2) / 2;
-		if (iv >= expand_bits(bits, (j << use_par) + odd)) i1 = j;
-		else i2 = j;
-	}
-	return (i1 << use_par) + odd;
-}
 // plane[j * 4 + w] = channel j of texels 4w .. 4w+3 (pads 0), all four channels
 A7_HD void window_planes_u8(const uint32_t *d, int n, uint32_t plane[16]) {
 #pragma unroll 1

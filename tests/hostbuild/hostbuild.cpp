@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 #include <atomic>
+#include <cmath>
 #endif
 
 #ifdef HB_BC1
@@ -198,6 +199,24 @@ template <int CLOG> static int hb_window_trial(uint64_t &rng, int size, int bits
 	const uint32_t a = window_item_u8<CLOG>(d, n, cur, q, p, size, bits_total, dim, ea);
 	const uint32_t b = window_item_lut_u8<CLOG>(lut.data(), d, plane, n, cur, q, p, size, bits_total, dim, eb);
 	return (a != b || ea != eb) ? 1 : 0;
+}
+// endpoint_floor_int (closed form) against endpoint_floor (the reference's bisection): every endpoint width, parity class and
+// a dense set of values around every integer of -2 .. 258 (and NaN). Returns the number of mismatches.
+extern "C" int hb_floor_check() {
+	using namespace b200ic::amd7;
+	int bad = 0;
+	for (int bits = 4; bits <= 8; bits++)
+		for (int use_par = 0; use_par <= 1; use_par++)
+			for (int odd = 0; odd <= 1; odd++) {
+				for (int i = -2 * 8; i <= 258 * 8; i++) {
+					const double v = (double) i / 8.0;
+					for (double dv : {0.0, 1e-9, -1e-9})
+						if (endpoint_floor_int(v + dv, bits, use_par, odd) != endpoint_floor(v + dv, bits, use_par, odd)) bad++;
+				}
+				const double nan = std::nan("");
+				if (endpoint_floor_int(nan, bits, use_par, odd) != endpoint_floor(nan, bits, use_par, odd)) bad++;
+			}
+	return bad;
 }
 extern "C" int hb_window_check(uint64_t seed, int trials) {
 	using namespace b200ic::amd7;

@@ -120,3 +120,11 @@ def test_cube_lane_mapping_matches_serial_walk():
     import hostbuild
     L = hostbuild.load()
     assert L.hb_cube_lane_check(7, 4000) == 0
+
+
+def test_endpoint_floor_closed_form():
+    """ep_find_floor (src/amd_shake.cpp:351-367) in closed form (bc7amd_int.cuh endpoint_floor_int, what the cube and window
+    kernels run) against the bisection, exhaustively over widths, parity classes and values."""
+    import hostbuild
+    L = hostbuild.load()
+    assert L.hb_floor_check() == 0
