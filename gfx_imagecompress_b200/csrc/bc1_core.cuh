@@ -347,15 +347,43 @@ B1_HDN void fit_endpoints(float result[3][2], const float in255[16][3], const fl
 			float pos[2] = {0.f, 0.f};
 			float lp = ls;
 			for (int l = 0; l < 8; l++, lp += stp) {
-				float hp = he;
-				for (int h = 0; h < 8; h++, hp -= stp) {
-					const float e = ramp_error(prj, prj_err, rep, lp, hp, n, np);
-					if (e < err) {
-						err = e;
-						pos[0] = lp;
-						pos[1] = hp;
+				// the 8 candidates of a row together: every texel is loaded once per row instead of once per candidate (the
+				// three per-texel arrays live in local memory; the search was waiting on those loads).  Each candidate's sum
+				// still runs over the texels in order, the candidates are compared in scan order.
+				float hps[8], e8[8], step8[8], steph8[8], rstep8[8];
+				{
+					float hp = he;
+#pragma unroll
+					for (int h = 0; h < 8; h++, hp -= stp) {
+						hps[h] = hp;
+						e8[h] = 0;
+						step8[h] = (hp - lp) / (float) (np - 1);
+						steph8[h] = step8[h] * 0.5f;
+						rstep8[h] = 1.0f / step8[h];
 					}
 				}
+#pragma unroll 1
+				for (int i = 0; i < n; i++) {
+					const float pi = prj[i], ri = rep[i], pe = prj_err[i];
+					const float del = pi - lp;
+#pragma unroll
+					for (int h = 0; h < 8; h++) {
+						float v;
+						if (del <= 0) v = lp;
+						else if (pi - hps[h] >= 0) v = hps[h];
+						else v = floorf((del + steph8[h]) * rstep8[h]) * step8[h] + lp;
+						float d = pi - v;
+						d *= d;
+						e8[h] += ri * d + pe;
+					}
+				}
+#pragma unroll
+				for (int h = 0; h < 8; h++)
+					if (e8[h] < err) {
+						err = e8[h];
+						pos[0] = lp;
+						pos[1] = hps[h];
+					}
 			}
 			for (int k = 0; k < 2; k++) pos[k] = pos[k] * (scl1 - scl0) + scl0;
 			if ((double) err + 0.001 < (double) err_g) {
