@@ -54,7 +54,7 @@ __device__ __forceinline__ void gather_block(const SrcImage &img, uint64_t block
 	}
 }
 
-__global__ void __launch_bounds__(kThreads) bc1_kernel(const Bc1Params p) {
+__global__ void __launch_bounds__(kThreads, 8) bc1_kernel(const Bc1Params p) {
 	// two adjacent lanes per block: the 3-point and the 4-point fit are independent until the final comparison.
 	// No early return: the pair meets in a shuffle below, so out-of-range pairs work on a clamped block and only skip
 	// the store (kThreads is even: pairs never straddle warps).
