@@ -584,7 +584,7 @@ def bench_sharded_image(args, g, torch, dist, codec, size, rank, local_rank, wor
             "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[codec], "data": "synthetic",
             "config": {"workload": f"{cname} encode of ONE {wl['name']} (BASELINE config[{BASE_CFG[codec]}] shape), block-rows sharded over "
-                                   f"{world} ranks by b200ic_plan_shards (chunks of 64 block-rows, largest first); no data-path collective",
+                                   f"{world} ranks by b200ic_plan_shards (chunks of 64 block-rows, one contiguous run per rank); no data-path collective",
                        "codec": cname, "image": [size, size], "rank0_block_rows": my_rows,
                        "l2_policy": f"input {host.nbytes >> 20} MiB per step exceeds the 126 MB L2"},
             "e2e": {"value": mpix_step * args.steps / float(e2e_s.item()), "unit": "Mpix/s",

@@ -649,18 +649,22 @@ uint64_t b200ic_plan_shards(const uint32_t *widths, const uint32_t *heights, uin
 			chunks.push_back({(uint64_t) bx * (r1 - r), (uint32_t) i, r, r1});
 		}
 	}
-	// largest first; equal sizes keep (image, row) order so that the plan is a pure function of the dimensions
-	std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk &a, const Chunk &b) { return a.blocks > b.blocks; });
-	std::vector<uint64_t> load(world, 0);
+	// Contiguous partition of the chunk sequence (image order, then row order): a chunk goes to the rank in whose share
+	// [r T / world, (r + 1) T / world) of the T blocks its midpoint falls.  Every rank gets one contiguous run (adjacent
+	// chunks of an image merge into one shard below: fewer, larger launches than a round-robin deal) and the loads differ by
+	// at most one chunk.  A pure function of the dimensions.
+	uint64_t total = 0;
+	for (const Chunk &c : chunks) total += c.blocks;
 	std::vector<Chunk> mine;
+	uint64_t before = 0;
 	for (const Chunk &c : chunks) {
-		uint32_t best = 0;
-		for (uint32_t r = 1; r < world; r++)
-			if (load[r] < load[best]) best = r;
-		load[best] += c.blocks;
-		if (best == rank) mine.push_back(c);
+		// rank = floor((before + blocks / 2) * world / total), in 128-bit-safe form (total < 2^40, world < 2^16)
+		const uint64_t mid2 = 2 * before + c.blocks; // twice the midpoint
+		uint64_t r = total ? (uint64_t) (((unsigned __int128) mid2 * world) / (2 * (unsigned __int128) total)) : 0;
+		if (r >= world) r = world - 1;
+		if (r == rank) mine.push_back(c);
+		before += c.blocks;
 	}
-	std::sort(mine.begin(), mine.end(), [](const Chunk &a, const Chunk &b) { return a.image != b.image ? a.image < b.image : a.row0 < b.row0; });
 	uint64_t n = 0;
 	b200ic_shard cur = {0, 0, 0, 0};
 	bool have = false;

@@ -148,9 +148,10 @@ typedef struct b200ic_shard {
 } b200ic_shard;
 
 /* Deterministic partition of the block-rows of `n_images` images over `world` ranks (every rank computes the same
- * plan, no communication): images are cut into chunks of at most `chunk_rows` block-rows (0 = 64), the chunks are
- * dealt largest-first to the least loaded rank (ties to the lowest rank), and each rank's chunks are returned sorted
- * by (image, row0) with adjacent ranges merged.  Blocks are independent, so the encode needs no halo and no
+ * plan, no communication): images are cut into chunks of at most `chunk_rows` block-rows (0 = 64); rank r takes the
+ * chunks (in image, row order) whose midpoint falls into its share [r T / world, (r + 1) T / world) of the T blocks -- one
+ * contiguous run per rank, loads within one chunk of each other -- returned sorted by (image, row0) with adjacent ranges
+ * merged.  Blocks are independent, so the encode needs no halo and no
  * collective.  Writes at most `cap` shards of `rank` to `out` and returns how many it has.  Host-only. */
 B200IC_API uint64_t b200ic_plan_shards(const uint32_t *widths, const uint32_t *heights, uint64_t n_images, uint32_t chunk_rows,
 																			 uint32_t world, uint32_t rank, b200ic_shard *out, uint64_t cap);
