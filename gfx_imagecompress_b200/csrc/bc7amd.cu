@@ -9,18 +9,22 @@
 // error (= the reference's first strict minimum).  8-bit sources (every component an exact integer) take the phase
 // kernels below; float sources the generic FP64 kernel at the end of the file.
 //
-// Partitioned modes 0, 1, 2, 3, 7 -- THREE kernels per mode, one warp per 4x4 block, state handed over through HBM
+// Modes 0 .. 5 and 7 -- THREE kernels per mode (two for mode 7, which has no cube walk), state handed over through HBM
 // (<= 584 B per block: traffic that is 10^-3 of the ALU time, and every phase gets its own register budget / occupancy):
-//   quantise : lane = (partition, subset): 48 .. 192 independent optQuantAnD problems per block (FP64), ranking of the
-//              partitions, the 8 best are kept                                   -> q_top, q_idx
-//   cube     : ep_shaker_d (82 % of the reference's time).  A work item = (task, (q,p) re-indexing); set-up (cluster
-//              statistics, least-squares fit, lattice floors) one item per lane, then the items one after the other with
-//              lane = (lattice, corner): all 32 lanes share the texels (registers), the trip count and the ramp tables
-//              (shared memory) -- no divergence in the 3-instruction inner loop (VABSDIFF4, IDP.4A, VIMNMX3); winners by
-//              redux.sync min of (error, scan position) keys = the reference's first strict minimum
-//                                                                                -> c_idx, c_err
-//   window   : ep_shaker_2_d chains (lane = (task, (q,p)) item), best attempt, bit packing, compare-and-store
-// Modes 4, 5, 6 (16 / 8 / 1 independent tasks per block, all on 16 texels): thread per block, serial form.
+//   quantise : lane = one optQuantAnD problem (FP64): a (partition, subset) of the block -- 48 .. 192 per block, repeated
+//              subsets of the 3-subset tables once -- or a (rotation, index selection, vector | scalar) of 2 / 4 blocks
+//              (modes 4 / 5); ranking of the partitions, the 8 best are kept          -> q_top, q_idx
+//   cube     : ep_shaker_d (82 % of the reference's time).  Persistent warps take the next block -- the next 2 / 4 blocks
+//              in the modes with 16 / 8 tasks per block -- from the launch's work counter.  A work item = (task, (q,p)
+//              re-indexing); set-up (cluster statistics, least-squares fit, lattice floors) one item per lane, then the
+//              items one after the other with lane = (lattice, corner): all 32 lanes share the texels, the trip count and
+//              the ramp tables (shared memory) -- no divergence in the 3-instruction inner loop (VABSDIFF4, IDP.4A,
+//              VIMNMX3); winners by redux.sync min of (error, scan position) keys = the reference's first strict minimum;
+//              mode 0 prunes its second pass with per-channel bounds               -> c_idx, c_err
+//   window   : ep_shaker_2_d chains (fit: lane = item; search: lane = (item, channel, parity combination)), best attempt,
+//              bit packing, compare-and-store
+// The kernels are instantiated per index width (and pruning): the code a mode never runs is compiled out (instruction cache).
+// Mode 6 (ONE task per block, 16 index levels): thread per block, serial form.
 #include "common.cuh"
 #include "kernels.h"
 #include "bc7amd_block.cuh"
@@ -1274,10 +1278,9 @@ static_assert(sizeof(WindowScratch1) <= kWindowSmemBudget && sizeof(WindowScratc
 							"window scratch: 2 CTAs per SM");
 
 // =====================================================================================================================
-// Modes with few independent tasks per block -- mode 6: ONE partition, ONE subset; modes 4 / 5: 16 / 8 (rotation,
-// index selection, vector | scalar) tasks -- leave most lanes of a warp-per-block mapping idle.  For these every
-// THREAD takes a block and runs the serial form of the same search (bc7amd_block.cuh, the code the host build checks
-// against the reference).
+// Mode 6 has ONE task per block (one partition, one subset, 16 index levels: outside the 8-entry ramp words of the window
+// kernel): every THREAD takes a block and runs the serial form of the same search (bc7amd_block.cuh, the code the host
+// build checks against the reference).  1.4 % of the benchmark step.  (Debug builds can route modes 4 / 5 here too.)
 // =====================================================================================================================
 __global__ void __launch_bounds__(128) bc7amd_serial_kernel(const AmdParams p, const int mode) {
 	const uint32_t block = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1716,7 +1719,7 @@ cudaError_t launch_bc7amd(const SrcImage &img, const b200ic_opts &opts, void *ds
 	}
 	const uint32_t user = p.mode_mask ? p.mode_mask : 0xCFu;
 	int launches = 0;
-	for (uint64_t b0 = 0; b0 < total_blocks; b0 += chunk) {
+	for (uint64_t b0 = 0; b0 < total_blocks && e == cudaSuccess; b0 += chunk) {
 		p.block0 = b0;
 		p.n_blocks = (uint32_t) (total_blocks - b0 < chunk ? total_blocks - b0 : chunk);
 		const unsigned warp_grid = (p.n_blocks + kWarps - 1) / kWarps;
